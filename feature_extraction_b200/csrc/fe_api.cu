@@ -1,0 +1,991 @@
+// fe_api.cu — host side of libfe_b200.so: context, parameter derivation, sub-batch pipeline and
+// the C-ABI of include/fe_b200.h.  No CPU fallback anywhere: every entry point that computes
+// launches the kernels of fe_kernels.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "fe_kernels.cuh"
+
+using namespace fe;
+
+#define FE_VERSION "fe_b200 0.1 (sm_100a)"
+
+namespace {
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  int64_t capPts = 0;
+  int capScans = 0, capChunks = 0;
+  int64_t capKp = 0;
+  int capKf = 0, capKc = 0;
+  // device
+  float4 *d_pts = nullptr, *d_surf = nullptr, *d_crop = nullptr, *d_sorted = nullptr, *d_full = nullptr;
+  unsigned *d_cropMeta = nullptr, *d_keyA = nullptr, *d_keyB = nullptr, *d_valA = nullptr, *d_valB = nullptr, *d_sortedKey = nullptr;
+  int* d_rho = nullptr;
+  long long* d_scan_off = nullptr;
+  int *d_chunk_off = nullptr, *d_surfCnt = nullptr, *d_cropCnt = nullptr;
+  float* d_rot = nullptr;
+  int *d_kfBase = nullptr, *d_kfCnt = nullptr, *d_kcBase = nullptr, *d_kcCnt = nullptr;
+  int *d_kpBase = nullptr, *d_kpCnt = nullptr, *d_kpOff = nullptr, *d_kpScan = nullptr, *d_kpNbr = nullptr;
+  int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
+  int64_t capRowStart = 0;
+  float4 *d_kfPool = nullptr, *d_kcPool = nullptr, *d_kpPool = nullptr, *d_kpOut = nullptr, *d_gather = nullptr;
+  float* d_desc = nullptr;
+  DevCounters* d_ctr = nullptr;
+  // pinned host mirrors
+  long long* h_scan_off = nullptr;
+  int* h_chunk_off = nullptr;
+  float* h_rot = nullptr;
+  DevCounters* h_ctr = nullptr;
+  int* h_kpOff = nullptr;
+  int* h_perScan = nullptr;
+  cudaEvent_t evDone = nullptr;
+  // bookkeeping of the sub-batch in flight
+  int nscans = 0;
+  int64_t npts = 0;
+  int firstScan = 0;
+  bool busy = false;
+  // stage timing
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> evName;
+  int nev = 0;
+};
+
+}  // namespace
+
+struct fe_ctx {
+  int device = 0;
+  fe_params_t params;
+  DevParams dp;
+  fe_limits_t lim;
+  Slot slot[2];
+  float* d_lut = nullptr;
+  float2* d_axes = nullptr;
+  int axesCap = 0;
+  bool cloudOutputs = false;
+  // results (host, pinned, grown on demand)
+  std::vector<int64_t> kpOffsets;
+  fe_point_t* h_kp = nullptr;
+  float* h_desc = nullptr;
+  int64_t capResKp = 0, capResDesc = 0;
+  // optional cloud outputs of the last single-sub-batch call
+  std::vector<int64_t> cloudOff, kcOff;
+  std::vector<fe_point_t> cloudPts, kcPts;
+  // stage times of the last device call
+  std::vector<const char*> stName;
+  std::vector<float> stMs;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      char b_[512];                                                                    \
+      snprintf(b_, sizeof b_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = b_;                                                                   \
+      return FE_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+int fail(fe_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+// ---- parameter derivation (host, float/double exactly as PCL narrows them) ------------------
+
+float radius_sq_as_flann_sees_it(double radius) { return (float)(radius * radius); }
+
+// pcl::ShapeContext3DEstimation::initCompute (3dsc.hpp): bin edges and the 1/cbrt(volume) table
+void shape_context_tables(double R, double rmin, float radii[16], float theta[12], float phi[13], float* lut) {
+  const int NA = 12, NE = 11, NR = 15;
+  const float az_step = 360.0f / (float)NA, el_step = 180.0f / (float)NE;
+  for (int j = 0; j <= NR; j++)
+    radii[j] = (float)exp(log(rmin) + (((float)j / (float)NR) * log(R / rmin)));
+  for (int k = 0; k <= NE; k++) theta[k] = (float)k * el_step;
+  for (int l = 0; l <= NA; l++) phi[l] = (float)l * az_step;
+  const float d2r = 0.017453293f;
+  const float dphi = phi[1] * d2r - phi[0] * d2r;
+  const float third = 1.0f / 3.0f;
+  for (int j = 0; j < NR; j++) {
+    const float dr = (radii[j + 1] * radii[j + 1] * radii[j + 1] / 3.0f) - (radii[j] * radii[j] * radii[j] / 3.0f);
+    for (int k = 0; k < NE; k++) {
+      const float dth = cosf(theta[k] * d2r) - cosf(theta[k + 1] * d2r);
+      const float V = dphi * dth * dr;
+      for (int l = 0; l < NA; l++) lut[l * NE * NR + k * NR + j] = 1.0f / powf(V, third);
+    }
+  }
+}
+
+// Eigen 3.2 AngleAxisf(pitch, Y) * AngleAxisf(roll, X) -> rotation matrix (row-major 3x3)
+void leveling_matrix(double roll, double pitch, float m[9]) {
+  const float hp = 0.5f * (float)pitch, hr = 0.5f * (float)roll;
+  // quaternions (w, x, y, z)
+  const float aw = cosf(hp), ax = 0.0f * sinf(hp), ay = 1.0f * sinf(hp), az = 0.0f * sinf(hp);
+  const float bw = cosf(hr), bx = 1.0f * sinf(hr), by = 0.0f * sinf(hr), bz = 0.0f * sinf(hr);
+  const float w = aw * bw - ax * bx - ay * by - az * bz;
+  const float x = aw * bx + ax * bw + ay * bz - az * by;
+  const float y = aw * by + ay * bw + az * bx - ax * bz;
+  const float z = aw * bz + az * bw + ax * by - ay * bx;
+  const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  float R[9];
+  R[0] = 1.0f - (tyy + tzz); R[1] = txy - twz;          R[2] = txz + twy;
+  R[3] = txy + twz;          R[4] = 1.0f - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;          R[7] = tyz + twx;          R[8] = 1.0f - (txx + tyy);
+  // Affine3f::Identity().rotate(q): Identity.linear() * R, 3-term sums as a0 + (a1 + a2)
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      const float i0 = (i == 0) ? 1.0f : 0.0f, i1 = (i == 1) ? 1.0f : 0.0f, i2 = (i == 2) ? 1.0f : 0.0f;
+      m[i * 3 + j] = i0 * R[j] + (i1 * R[3 + j] + i2 * R[6 + j]);
+    }
+}
+
+int bits_for_host(int v) { int b = 0; while (v > 0) { b++; v >>= 1; } return b; }
+
+// surface keep-box and 2-D grid for keypoints known to lie inside [x0,x1]x[y0,y1]x[z0,z1]
+void surface_grid(DevParams& dp, double R, float x0, float x1, float y0, float y1, float z0, float z1) {
+  const double rrho = R / 5.0;
+  const float reach = (float)((R + rrho) * 1.001 + 1e-3);
+  dp.sx0 = x0 - reach; dp.sx1 = x1 + reach;
+  dp.sy0 = y0 - reach; dp.sy1 = y1 + reach;
+  dp.sz0 = z0 - reach; dp.sz1 = z1 + reach;
+  float cell = (float)(rrho * 1.001);
+  if (!(cell > 1e-6f)) cell = 1e-6f;
+  const float ex = dp.sx1 - dp.sx0, ey = dp.sy1 - dp.sy0;
+  const float maxdim = 2047.0f;
+  if (ex / cell > maxdim) cell = ex / maxdim;
+  if (ey / cell > maxdim) cell = ey / maxdim;
+  dp.sg_inv = 1.0f / cell;
+  dp.sg_nx = std::max(1, std::min(2048, (int)floorf(ex * dp.sg_inv) + 1));
+  dp.sg_ny = std::max(1, std::min(2048, (int)floorf(ey * dp.sg_inv) + 1));
+  dp.sg_bx = std::max(1, bits_for_host(dp.sg_nx - 1));
+  dp.Rpad = (float)(R * 1.0001 + 1e-6);
+  dp.rhopad = (float)(rrho * 1.0001 + 1e-6);
+}
+
+int derive_params(fe_ctx* ctx, const fe_params_t& p) {
+  if (!(p.descriptor_radius > 0.0) || !(p.cluster_tolerance > 0.0) || !(p.cluster_radius_threshold > 0.0))
+    return fail(ctx, FE_ERR_INVALID, "cluster_tolerance, cluster_radius_threshold and descriptor_radius must be > 0");
+  DevParams& dp = ctx->dp;
+  memset(&dp, 0, sizeof dp);
+  dp.xmin = (float)p.x_min; dp.xmax = (float)p.x_max;
+  dp.ymin = (float)p.y_min; dp.ymax = (float)p.y_max;
+  dp.zmin = (float)p.z_min; dp.zmax = (float)p.z_max;
+  dp.tol_f = (float)p.cluster_tolerance;
+  dp.r2f_cluster = radius_sq_as_flann_sees_it((double)dp.tol_f);
+  dp.min_count = p.cluster_min_count;
+  dp.max_count = p.cluster_max_count;
+  dp.two_radius_threshold = 2 * p.cluster_radius_threshold;
+  dp.radius_threshold = p.cluster_radius_threshold;
+  dp.merge_tol_f = (float)p.cluster_radius_threshold;
+  dp.r2f_merge = radius_sq_as_flann_sees_it((double)dp.merge_tol_f);
+  dp.min_channels = p.number_detection_channels;
+  dp.R2f = radius_sq_as_flann_sees_it(p.descriptor_radius);
+  dp.rho2f = radius_sq_as_flann_sees_it(p.descriptor_radius / 5.0);
+  dp.estimate_descriptors = p.estimate_descriptors;
+  std::vector<float> lut(FE_DESC_LEN);
+  shape_context_tables(p.descriptor_radius, p.descriptor_radius / 10.0, dp.radii, dp.theta, dp.phi, lut.data());
+  surface_grid(dp, p.descriptor_radius, dp.xmin, dp.xmax, dp.ymin, dp.ymax, dp.zmin, dp.zmax);
+  CK(cudaMemcpy(ctx->d_lut, lut.data(), FE_DESC_LEN * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->params = p;
+  return FE_OK;
+}
+
+// ---- slot allocation ---------------------------------------------------------------------------
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+template <class T>
+cudaError_t halloc(T** p, size_t n) { return cudaHostAlloc((void**)p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault); }
+
+void free_slot(Slot& s) {
+  void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
+                s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
+                s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_rowStart,
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
+  for (void* p : dv) if (p) cudaFree(p);
+  void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
+  for (void* p : hv) if (p) cudaFreeHost(p);
+  for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+  if (s.evDone) cudaEventDestroy(s.evDone);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s = Slot();
+}
+
+int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
+  if (s.stream) {
+    if (ownPoints && !s.d_pts) CK(dalloc(&s.d_pts, (size_t)s.capPts));
+    return FE_OK;
+  }
+  const fe_limits_t& L = ctx->lim;
+  s.capPts = L.max_points_per_call;
+  s.capScans = L.max_scans_per_call;
+  s.capChunks = (int)(s.capPts / CH) + s.capScans + 1;
+  s.capKp = L.max_keypoints_per_call;
+  s.capKf = (int)L.max_ring_clusters_per_call;
+  s.capKc = 0;
+  CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming));
+  const size_t np = (size_t)s.capPts, ns = (size_t)s.capScans;
+  if (ownPoints) CK(dalloc(&s.d_pts, np));
+  CK(dalloc(&s.d_surf, np)); CK(dalloc(&s.d_crop, np)); CK(dalloc(&s.d_sorted, np));
+  CK(dalloc(&s.d_cropMeta, np)); CK(dalloc(&s.d_keyA, np)); CK(dalloc(&s.d_keyB, np));
+  CK(dalloc(&s.d_valA, np)); CK(dalloc(&s.d_valB, np)); CK(dalloc(&s.d_sortedKey, np));
+  CK(dalloc(&s.d_rho, np));
+  CK(dalloc(&s.d_scan_off, ns + 1)); CK(dalloc(&s.d_chunk_off, ns + 1));
+  CK(dalloc(&s.d_surfCnt, (size_t)s.capChunks)); CK(dalloc(&s.d_cropCnt, (size_t)s.capChunks));
+  CK(dalloc(&s.d_rot, ns * 9));
+  CK(dalloc(&s.d_kfBase, ns * 16)); CK(dalloc(&s.d_kfCnt, ns * 16));
+  CK(dalloc(&s.d_kcBase, ns * 16)); CK(dalloc(&s.d_kcCnt, ns * 16));
+  CK(dalloc(&s.d_kpBase, ns)); CK(dalloc(&s.d_kpCnt, ns)); CK(dalloc(&s.d_kpOff, ns + 1));
+  CK(dalloc(&s.d_kpScan, (size_t)s.capKp)); CK(dalloc(&s.d_kpNbr, (size_t)s.capKp));
+  CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1));
+  CK(dalloc(&s.d_kfPool, (size_t)s.capKf)); CK(dalloc(&s.d_kpPool, (size_t)s.capKp)); CK(dalloc(&s.d_kpOut, (size_t)s.capKp));
+  CK(dalloc(&s.d_desc, (size_t)s.capKp * FE_DESC_LEN));
+  CK(dalloc(&s.d_ctr, 1));
+  CK(halloc(&s.h_scan_off, ns + 1)); CK(halloc(&s.h_chunk_off, ns + 1)); CK(halloc(&s.h_rot, ns * 9));
+  CK(halloc(&s.h_ctr, 1)); CK(halloc(&s.h_kpOff, ns + 1)); CK(halloc(&s.h_perScan, ns + 1));
+  s.ev.resize(24);
+  for (auto& e : s.ev) CK(cudaEventCreate(&e));
+  s.evName.assign(24, "");
+  return FE_OK;
+}
+
+void mark(fe_ctx* ctx, Slot& s, const char* name) {
+  if (s.nev < (int)s.ev.size()) {
+    cudaEventRecord(s.ev[s.nev], s.stream);
+    s.evName[s.nev] = name;
+    s.nev++;
+  }
+  (void)ctx;
+}
+
+std::string err_bits(int e) {
+  std::string m;
+  if (e & ERR_RING_CAP) m += "one ring of a scan holds more cluster entries than the shared-memory capacity; ";
+  if (e & ERR_KF_POOL) m += "ring-centroid pool exhausted (raise max_ring_clusters_per_call); ";
+  if (e & ERR_KP_POOL) m += "keypoint pool exhausted (raise max_keypoints_per_call); ";
+  if (e & ERR_MERGE_CAP) m += "a scan has more ring centroids than the merge capacity; ";
+  if (e & ERR_AXIS_CAP) m += "a scan has more keypoints than precomputed 3DSC axes; ";
+  if (e & ERR_CHUNKS) m += "a scan has more points than the per-scan kernels index; ";
+  if (e & ERR_KC_POOL) m += "keypoint_cloud pool exhausted; ";
+  return m;
+}
+
+// Host-side staging of the small per-scan arrays of a sub-batch.  offs are absolute offsets of
+// the caller's array; the device sees offsets relative to the first point of the sub-batch.
+int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int nscans, int64_t* nptsOut, int* nchOut) {
+  const int64_t o0 = offs[0];
+  int nch = 0;
+  for (int i = 0; i < nscans; i++) {
+    const int64_t n = offs[i + 1] - offs[i];
+    if (n < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must be non-decreasing");
+    s.h_scan_off[i] = (long long)(offs[i] - o0);
+    s.h_chunk_off[i] = nch;
+    nch += (int)((n + CH - 1) / CH);
+    if (rp) leveling_matrix(rp[2 * i], rp[2 * i + 1], s.h_rot + 9 * i);
+    else { float* m = s.h_rot + 9 * i; for (int k = 0; k < 9; k++) m[k] = (k % 4 == 0) ? 1.0f : 0.0f; }
+  }
+  s.h_scan_off[nscans] = (long long)(offs[nscans] - o0);
+  s.h_chunk_off[nscans] = nch;
+  *nptsOut = offs[nscans] - o0;
+  *nchOut = nch;
+  if (*nptsOut > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_points_per_call");
+  if (nscans > s.capScans) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_scans_per_call");
+  if (nch > s.capChunks) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds the chunk capacity");
+  CK(cudaMemcpyAsync(s.d_scan_off, s.h_scan_off, (nscans + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+  CK(cudaMemcpyAsync(s.d_chunk_off, s.h_chunk_off, (nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  CK(cudaMemcpyAsync(s.d_rot, s.h_rot, (size_t)nscans * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+  return FE_OK;
+}
+
+int ensure_rowstart(fe_ctx* ctx, Slot& s, int nscans) {
+  const int64_t need = (int64_t)std::max(nscans, s.capScans) * (ctx->dp.sg_ny + 1);
+  if (need > s.capRowStart) {
+    if (s.d_rowStart) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.d_rowStart)); s.d_rowStart = nullptr; }
+    CK(dalloc(&s.d_rowStart, (size_t)need));
+    s.capRowStart = need;
+  }
+  return FE_OK;
+}
+
+int ensure_kc(fe_ctx* ctx, Slot& s) {
+  if (s.capKc == 0) {
+    s.capKc = (int)std::min<int64_t>(s.capPts, 1 << 26);
+    CK(dalloc(&s.d_kcPool, (size_t)s.capKc));
+    CK(dalloc(&s.d_gather, (size_t)s.capPts));
+  }
+  return FE_OK;
+}
+
+const size_t kClusterSmem = cluster_smem_bytes();
+
+int set_kernel_attrs(fe_ctx* ctx) {
+  CK(cudaFuncSetAttribute(k_cluster_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_merge_keypoints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  return FE_OK;
+}
+
+// Enqueue the kernels of one sub-batch whose points are at d_pts.  k1flags selects what K1 does;
+// `fromStage`: 0 = K1 first; 1 = crop/cropMeta/cropCnt already filled by the caller.
+int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int64_t npts, int nch,
+                     int k1flags, bool doDesc, bool singleRing, bool wantKc) {
+  DevParams& P = ctx->dp;
+  s.nev = 0;
+  mark(ctx, s, "begin");
+  CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), s.stream));
+  if (nch > 0 && k1flags >= 0) {
+    k_level_crop_ring<<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+                                                 s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr);
+    ctx->launches++;
+  }
+  mark(ctx, s, "K1 level+crop+ring");
+  k_cluster_rings<<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
+                                                           singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt,
+                                                           wantKc ? s.d_kcPool : nullptr, s.capKc, wantKc ? s.d_kcBase : nullptr,
+                                                           wantKc ? s.d_kcCnt : nullptr, s.d_ctr);
+  ctx->launches++;
+  mark(ctx, s, "K2 ring clusters");
+  k_merge_keypoints<<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
+                                                             s.d_kpBase, s.d_kpCnt, nullptr, nullptr, s.d_ctr);
+  ctx->launches++;
+  k_kp_offsets<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr);
+  ctx->launches++;
+  k_kp_gather<<<std::max(1, std::min(1024, (nscans * 8 + 255) / 256)), 256, 0, s.stream>>>(s.d_kpPool, s.d_kpBase, s.d_kpOff, nscans,
+                                                                                            s.d_kpOut, s.d_kpScan);
+  ctx->launches++;
+  mark(ctx, s, "K3 merge keypoints");
+  if (doDesc) {
+    int st = ensure_rowstart(ctx, s, nscans);
+    if (st) return st;
+    CK(cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(npts, 1) * sizeof(int), s.stream));
+    k_surface_grid<<<nscans, NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA,
+                                                 s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr);
+    ctx->launches++;
+    mark(ctx, s, "K4a surface grid");
+    const int gridKp = 148 * 8;
+    k_desc_mark<<<gridKp, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, s.d_sortedKey, s.d_rowStart,
+                                              s.d_scan_off, P, s.d_rho, s.d_kpNbr);
+    ctx->launches++;
+    mark(ctx, s, "K4b mark neighbours");
+    if (npts > 0) {
+      const int gridD = (int)std::min<int64_t>((npts + 255) / 256, 148 * 64);
+      k_density<<<gridD, 256, 0, s.stream>>>(s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P, (long long)npts, s.d_rho);
+      ctx->launches++;
+    }
+    mark(ctx, s, "K4c density");
+    k_desc_hist<<<gridKp, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, s.d_sortedKey,
+                                              s.d_rowStart, s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap,
+                                              s.d_desc, s.d_ctr);
+    ctx->launches++;
+    mark(ctx, s, "K4d shape context");
+  }
+  CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaMemcpyAsync(s.h_kpOff, s.d_kpOff, (size_t)(nscans + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaEventRecord(s.evDone, s.stream));
+  CK(cudaGetLastError());
+  return FE_OK;
+}
+
+void collect_times(fe_ctx* ctx, Slot& s) {
+  ctx->stName.clear();
+  ctx->stMs.clear();
+  for (int i = 1; i < s.nev; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.ev[i - 1], s.ev[i]) == cudaSuccess) {
+      ctx->stName.push_back(s.evName[i]);
+      ctx->stMs.push_back(ms);
+    }
+  }
+}
+
+int grow_results(fe_ctx* ctx, int64_t needKp, bool desc) {
+  if (needKp > ctx->capResKp) {
+    for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+    const int64_t cap = std::max<int64_t>(needKp * 3 / 2, 4096);
+    fe_point_t* nk = nullptr;
+    CK(halloc(&nk, (size_t)cap));
+    if (ctx->h_kp) { memcpy(nk, ctx->h_kp, (size_t)ctx->capResKp * sizeof(fe_point_t)); cudaFreeHost(ctx->h_kp); }
+    ctx->h_kp = nk;
+    ctx->capResKp = cap;
+  }
+  if (desc && ctx->capResKp > ctx->capResDesc) {
+    for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+    float* nd = nullptr;
+    CK(halloc(&nd, (size_t)ctx->capResKp * FE_DESC_LEN));
+    if (ctx->h_desc) { memcpy(nd, ctx->h_desc, (size_t)ctx->capResDesc * FE_DESC_LEN * sizeof(float)); cudaFreeHost(ctx->h_desc); }
+    ctx->h_desc = nd;
+    ctx->capResDesc = ctx->capResKp;
+  }
+  return FE_OK;
+}
+
+// wait for the sub-batch in `s`, check its error word, append its keypoints to the results
+int finalize_subbatch(fe_ctx* ctx, Slot& s, int64_t& kpRun, bool desc) {
+  if (!s.busy) return FE_OK;
+  CK(cudaEventSynchronize(s.evDone));
+  s.busy = false;
+  if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
+  const int K = s.h_kpOff[s.nscans];
+  int st = grow_results(ctx, kpRun + K, desc);
+  if (st) return st;
+  for (int i = 0; i <= s.nscans; i++) ctx->kpOffsets[s.firstScan + i] = kpRun + s.h_kpOff[i];
+  if (K > 0) {
+    CK(cudaMemcpyAsync(ctx->h_kp + kpRun, s.d_kpOut, (size_t)K * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
+    if (desc) CK(cudaMemcpyAsync(ctx->h_desc + kpRun * FE_DESC_LEN, s.d_desc, (size_t)K * FE_DESC_LEN * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+  }
+  kpRun += K;
+  return FE_OK;
+}
+
+int gather_to_host(fe_ctx* ctx, Slot& s, int nscans, bool chunks, const float4* src, const int* cnt, const int* pBase,
+                   std::vector<int64_t>& offOut, std::vector<fe_point_t>& ptsOut) {
+  if (chunks) k_piece_counts<<<(nscans + 255) / 256, 256, 0, s.stream>>>(cnt, s.d_chunk_off, nscans, s.d_perScan);
+  else k_pool16_counts<<<(nscans + 255) / 256, 256, 0, s.stream>>>(cnt, nscans, s.d_perScan);
+  ctx->launches++;
+  CK(cudaMemcpyAsync(s.h_perScan, s.d_perScan, (size_t)nscans * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  offOut.assign(nscans + 1, 0);
+  std::vector<int> off32(nscans + 1, 0);
+  for (int i = 0; i < nscans; i++) { offOut[i + 1] = offOut[i] + s.h_perScan[i]; off32[i + 1] = (int)offOut[i + 1]; }
+  const int64_t tot = offOut[nscans];
+  ptsOut.resize((size_t)tot);
+  if (tot == 0) return FE_OK;
+  if (tot > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "cloud output exceeds max_points_per_call");
+  CK(cudaMemcpyAsync(s.d_outOff, off32.data(), (size_t)(nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  if (chunks) k_gather_chunks<<<nscans, 256, 0, s.stream>>>(src, cnt, s.d_scan_off, s.d_chunk_off, s.d_outOff, s.d_gather);
+  else k_gather_pool16<<<nscans, 256, 0, s.stream>>>(src, pBase, cnt, s.d_outOff, s.d_gather);
+  ctx->launches++;
+  CK(cudaMemcpyAsync(ptsOut.data(), s.d_gather, (size_t)tot * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return FE_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* fe_version(void) { return FE_VERSION; }
+
+void fe_params_node_default(fe_params_t* p) {
+  p->x_min = 0.0; p->x_max = 75.0;
+  p->y_min = -30.0; p->y_max = 30.0;
+  p->z_min = -1.5; p->z_max = 5.0;
+  p->cluster_tolerance = 0.65;
+  p->cluster_min_count = 5;
+  p->cluster_max_count = 50;
+  p->cluster_radius_threshold = 0.15;
+  p->number_detection_channels = 1;
+  p->estimate_descriptors = 1;
+  p->descriptor_radius = 2.5;
+}
+
+void fe_params_launch_playback(fe_params_t* p) {
+  fe_params_node_default(p);
+  p->x_max = 100.0;
+  p->y_min = -50.0; p->y_max = 50.0;
+  p->z_max = 4.0;
+  p->cluster_tolerance = 1.0;
+  p->cluster_min_count = 1;
+  p->cluster_max_count = 1000;
+  p->cluster_radius_threshold = 0.2;
+  p->number_detection_channels = 2;
+}
+
+int fe_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void* fe_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void fe_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+const char* fe_last_error(const fe_ctx_t* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int fe_create(int device, const fe_params_t* params, const fe_limits_t* limits, fe_ctx_t** out) {
+  if (!out || !params) return FE_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return FE_ERR_NO_DEVICE;  // no CPU fallback
+  if (device < 0 || device >= n) return FE_ERR_INVALID;
+  fe_ctx* ctx = new fe_ctx();
+  ctx->device = device;
+  fe_limits_t L = {0, 0, 0, 0};
+  if (limits) L = *limits;
+  if (L.max_points_per_call <= 0) L.max_points_per_call = 32LL << 20;
+  if (L.max_scans_per_call <= 0) L.max_scans_per_call = 2048;
+  if (L.max_keypoints_per_call <= 0) L.max_keypoints_per_call = 64 << 10;
+  if (L.max_ring_clusters_per_call <= 0) L.max_ring_clusters_per_call = 1 << 20;
+  if (L.max_points_per_call >= (1LL << 32) - CH) { delete ctx; return FE_ERR_INVALID; }
+  ctx->lim = L;
+  auto bail = [&](int code) { fe_destroy(ctx); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(FE_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(FE_ERR_CUDA);
+  if (prop.major != 10) return bail(FE_ERR_NO_DEVICE);  // built for sm_100a only
+  if (cudaMalloc((void**)&ctx->d_lut, FE_DESC_LEN * sizeof(float)) != cudaSuccess) return bail(FE_ERR_CUDA);
+  // 3DSC x-axes: boost::uniform_01<mt19937>(12345) draws 3k..3k+2 -> (x0, x1, -0) normalised
+  ctx->axesCap = 1 << 16;
+  {
+    std::vector<float2> ax(ctx->axesCap);
+    std::mt19937 gen(12345u);
+    for (int k = 0; k < ctx->axesCap; k++) {
+      const float u0 = (float)((double)gen() * (1.0 / 4294967296.0));
+      const float u1 = (float)((double)gen() * (1.0 / 4294967296.0));
+      (void)gen();  // the third draw is overwritten by -(n.x*x0 + n.y*x1)/n.z = -0
+      const float z = -(0.0f * u0 + 0.0f * u1) / 1.0f;
+      const float inv = 1.0f / sqrtf(u0 * u0 + (u1 * u1 + z * z));
+      ax[k].x = u0 * inv;
+      ax[k].y = u1 * inv;
+    }
+    if (cudaMalloc((void**)&ctx->d_axes, ax.size() * sizeof(float2)) != cudaSuccess) return bail(FE_ERR_CUDA);
+    if (cudaMemcpy(ctx->d_axes, ax.data(), ax.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return bail(FE_ERR_CUDA);
+  }
+  int st = derive_params(ctx, *params);
+  if (st) { fe_destroy(ctx); return st; }
+  st = set_kernel_attrs(ctx);
+  if (st) { fe_destroy(ctx); return st; }
+  *out = ctx;
+  return FE_OK;
+}
+
+int fe_set_params(fe_ctx_t* ctx, const fe_params_t* params) {
+  if (!ctx || !params) return FE_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
+  return derive_params(ctx, *params);
+}
+
+void fe_destroy(fe_ctx_t* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int k = 0; k < 2; k++) free_slot(ctx->slot[k]);
+  if (ctx->d_lut) cudaFree(ctx->d_lut);
+  if (ctx->d_axes) cudaFree(ctx->d_axes);
+  if (ctx->h_kp) cudaFreeHost(ctx->h_kp);
+  if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+  delete ctx;
+}
+
+int fe_enable_cloud_outputs(fe_ctx_t* ctx, int32_t enable) {
+  if (!ctx) return FE_ERR_INVALID;
+  ctx->cloudOutputs = enable != 0;
+  return FE_OK;
+}
+
+int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_point_t** cloud,
+                         const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud) {
+  if (!ctx) return FE_ERR_INVALID;
+  if (ctx->cloudOff.empty()) return fail(ctx, FE_ERR_INVALID, "no cloud outputs recorded (enable them before a single-sub-batch call)");
+  if (cloud_offsets) *cloud_offsets = ctx->cloudOff.data();
+  if (cloud) *cloud = ctx->cloudPts.data();
+  if (kpcloud_offsets) *kpcloud_offsets = ctx->kcOff.data();
+  if (keypoint_cloud) *keypoint_cloud = ctx->kcPts.data();
+  return FE_OK;
+}
+
+int fe_get_stage_times(fe_ctx_t* ctx, int32_t cap, const char** names, float* ms, int32_t* n) {
+  if (!ctx || !n) return FE_ERR_INVALID;
+  const int m = std::min<int>(cap, (int)ctx->stName.size());
+  for (int i = 0; i < m; i++) { names[i] = ctx->stName[i]; ms[i] = ctx->stMs[i]; }
+  *n = m;
+  return FE_OK;
+}
+
+// ---- the fused path ------------------------------------------------------------------------------
+
+int fe_process_batch(fe_ctx_t* ctx, const fe_point_t* points, const int64_t* scan_offsets,
+                     const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out) {
+  if (!ctx || !out || n_scans < 0 || (n_scans > 0 && (!scan_offsets || !roll_pitch))) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  ctx->err.clear();
+  const bool desc = ctx->params.estimate_descriptors != 0;
+  const int64_t launches0 = ctx->launches;
+  ctx->kpOffsets.assign((size_t)n_scans + 1, 0);
+  ctx->cloudOff.clear(); ctx->kcOff.clear(); ctx->cloudPts.clear(); ctx->kcPts.clear();
+  int64_t kpRun = 0;
+  int first = 0, cur = 0;
+  int nsub = 0;
+  while (first < n_scans) {
+    Slot& s = ctx->slot[cur];
+    int st = ensure_slot(ctx, s, true);
+    if (st) return st;
+    // previous sub-batch of this slot must have been finalised (its device buffers are reused)
+    st = finalize_subbatch(ctx, s, kpRun, desc);
+    if (st) return st;
+    // greedy sub-batch
+    int last = first;
+    int64_t npts = 0;
+    while (last < n_scans && (last - first) < s.capScans) {
+      const int64_t n = scan_offsets[last + 1] - scan_offsets[last];
+      if (n < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must be non-decreasing");
+      if (n > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "a single scan exceeds max_points_per_call");
+      if (npts + n > s.capPts) break;
+      npts += n;
+      last++;
+    }
+    const int ns = last - first;
+    int64_t np2; int nch;
+    st = stage_scans(ctx, s, scan_offsets + first, roll_pitch + 2 * first, ns, &np2, &nch);
+    if (st) return st;
+    if (npts > 0)
+      CK(cudaMemcpyAsync(s.d_pts, points + scan_offsets[first], (size_t)npts * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
+    const bool wantKc = ctx->cloudOutputs;
+    if (wantKc) { st = ensure_kc(ctx, s); if (st) return st; }
+    st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, wantKc);
+    if (st) return st;
+    s.busy = true; s.nscans = ns; s.npts = npts; s.firstScan = first;
+    nsub++;
+    // the other slot's sub-batch was enqueued earlier: finalise it while this one runs
+    Slot& o = ctx->slot[cur ^ 1];
+    if (o.busy) { st = finalize_subbatch(ctx, o, kpRun, desc); if (st) return st; }
+    first = last;
+    cur ^= 1;
+  }
+  // drain in submission order
+  for (int k = 0; k < 2; k++) {
+    Slot& s = ctx->slot[cur ^ k];  // cur now points at the older one
+    int st = finalize_subbatch(ctx, s, kpRun, desc);
+    if (st) return st;
+  }
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+  if (nsub == 1) {
+    Slot& s = ctx->slot[0];
+    collect_times(ctx, s);
+    if (ctx->cloudOutputs) {
+      int st = gather_to_host(ctx, s, s.nscans, true, s.d_crop, s.d_cropCnt, nullptr, ctx->cloudOff, ctx->cloudPts);
+      if (st) return st;
+      st = gather_to_host(ctx, s, s.nscans, false, s.d_kcPool, s.d_kcCnt, s.d_kcBase, ctx->kcOff, ctx->kcPts);
+      if (st) return st;
+    }
+  }
+  out->n_scans = n_scans;
+  out->n_keypoints = kpRun;
+  out->keypoint_offsets = ctx->kpOffsets.data();
+  out->keypoints = ctx->h_kp;
+  out->descriptors = desc ? ctx->h_desc : nullptr;
+  out->on_device = 0;
+  out->gpu_launches = ctx->launches - launches0;
+  return FE_OK;
+}
+
+int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int64_t* scan_offsets,
+                            const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out) {
+  if (!ctx || !out || n_scans < 0 || (n_scans > 0 && (!scan_offsets || !roll_pitch || !d_points))) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  ctx->err.clear();
+  const bool desc = ctx->params.estimate_descriptors != 0;
+  const int64_t launches0 = ctx->launches;
+  Slot& s = ctx->slot[0];
+  int st = ensure_slot(ctx, s, false);
+  if (st) return st;
+  ctx->kpOffsets.assign((size_t)n_scans + 1, 0);
+  int64_t npts = 0; int nch = 0;
+  if (n_scans > 0) {
+    st = stage_scans(ctx, s, scan_offsets, roll_pitch, n_scans, &npts, &nch);
+    if (st) return st;
+    st = enqueue_pipeline(ctx, s, (const float4*)d_points + scan_offsets[0], n_scans, npts, nch,
+                          F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, false);
+    if (st) return st;
+    CK(cudaEventSynchronize(s.evDone));
+    if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
+    for (int i = 0; i <= n_scans; i++) ctx->kpOffsets[i] = s.h_kpOff[i];
+    collect_times(ctx, s);
+  }
+  out->n_scans = n_scans;
+  out->n_keypoints = ctx->kpOffsets[n_scans];
+  out->keypoint_offsets = ctx->kpOffsets.data();
+  out->keypoints = (const fe_point_t*)s.d_kpOut;
+  out->descriptors = desc ? s.d_desc : nullptr;
+  out->on_device = 1;
+  out->gpu_launches = ctx->launches - launches0;
+  return FE_OK;
+}
+
+// ---- one entry point per reference function ----------------------------------------------------------
+
+static int stage_k1(fe_ctx* ctx, fe_point_t* cloud, int64_t n, double roll, double pitch, int flags) {
+  // K1 with full_out: every point transformed in place (no compaction)
+  Slot& s = ctx->slot[0];
+  int st = ensure_slot(ctx, s, true);
+  if (st) return st;
+  if (n == 0) return FE_OK;
+  if (!s.d_full) CK(dalloc(&s.d_full, (size_t)s.capPts));
+  int64_t offs[2] = {0, n};
+  double rp[2] = {roll, pitch};
+  int64_t npts; int nch;
+  st = stage_scans(ctx, s, offs, rp, 1, &npts, &nch);
+  if (st) return st;
+  CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
+  k_level_crop_ring<<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+                                               s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(cloud, s.d_full, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return FE_OK;
+}
+
+int fe_get_elevation_angles(fe_ctx_t* ctx, fe_point_t* cloud, int64_t n) {
+  if (!ctx || (n > 0 && !cloud) || n < 0) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return stage_k1(ctx, cloud, n, 0.0, 0.0, F_ELEV);
+}
+
+int fe_rotate_cloud(fe_ctx_t* ctx, fe_point_t* cloud, int64_t n, double roll, double pitch) {
+  if (!ctx || (n > 0 && !cloud) || n < 0) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return stage_k1(ctx, cloud, n, roll, pitch, F_ROT);
+}
+
+int fe_rotation_matrix(double roll, double pitch, float m[9]) {
+  if (!m) return FE_ERR_INVALID;
+  leveling_matrix(roll, pitch, m);
+  return FE_OK;
+}
+
+// upload a one-scan cloud and run K1 with the given flags (compacting into the chunk pieces)
+static int stage_upload_k1(fe_ctx* ctx, Slot& s, const fe_point_t* in, int64_t n, int flags, int* nchOut) {
+  int64_t offs[2] = {0, n};
+  int64_t npts;
+  int st = stage_scans(ctx, s, offs, nullptr, 1, &npts, nchOut);
+  if (st) return st;
+  if (n > 0) CK(cudaMemcpyAsync(s.d_pts, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
+  if (*nchOut > 0) {
+    k_level_crop_ring<<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+                                                     s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return FE_OK;
+}
+
+static int copy_points_out(fe_ctx* ctx, const std::vector<fe_point_t>& v, fe_point_t* out, int64_t cap, int64_t* n_out) {
+  if (n_out) *n_out = (int64_t)v.size();
+  if (!out) return FE_OK;
+  if ((int64_t)v.size() > cap) return fail(ctx, FE_ERR_CAPACITY, "output buffer too small");
+  if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(fe_point_t));
+  return FE_OK;
+}
+
+int fe_filter_cloud(fe_ctx_t* ctx, const fe_point_t* in, int64_t n, fe_point_t* out, int64_t cap, int64_t* n_out) {
+  if (!ctx || n < 0 || (n > 0 && !in)) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (n_out) *n_out = 0;
+  if (n == 0) return FE_OK;
+  Slot& s = ctx->slot[0];
+  int st = ensure_slot(ctx, s, true);
+  if (st) return st;
+  st = ensure_kc(ctx, s);
+  if (st) return st;
+  int nch;
+  st = stage_upload_k1(ctx, s, in, n, F_CROP, &nch);
+  if (st) return st;
+  std::vector<int64_t> off;
+  std::vector<fe_point_t> pts;
+  st = gather_to_host(ctx, s, 1, true, s.d_crop, s.d_cropCnt, nullptr, off, pts);
+  if (st) return st;
+  return copy_points_out(ctx, pts, out, cap, n_out);
+}
+
+int fe_extract_clusters(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, double tolerance,
+                        int32_t min_size, int32_t max_size, int32_t* cluster_offsets,
+                        int32_t cap_clusters, int32_t* indices, int64_t cap_indices, int32_t* n_clusters) {
+  if (!ctx || n < 0 || (n > 0 && !cloud) || !n_clusters || !cluster_offsets) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  *n_clusters = 0;
+  cluster_offsets[0] = 0;
+  if (n == 0) return FE_OK;
+  if (n > ECAP) return fail(ctx, FE_ERR_CAPACITY, "fe_extract_clusters: cloud larger than the per-block capacity");
+  if (!(tolerance > 0.0)) return fail(ctx, FE_ERR_INVALID, "tolerance must be > 0");
+  Slot& s = ctx->slot[0];
+  int st = ensure_slot(ctx, s, true);
+  if (st) return st;
+  CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
+  const float tol_f = (float)tolerance;
+  const float r2f = radius_sq_as_flann_sees_it((double)tol_f);
+  int* d_off = (int*)s.d_keyA;
+  int* d_idx = (int*)s.d_keyB;
+  int* d_n = (int*)s.d_valA;
+  k_extract_clusters_stage<<<1, NT2, kClusterSmem, s.stream>>>(s.d_pts, (int)n, tol_f, r2f, min_size, max_size, d_off, (int)n, d_idx, d_n);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  int nc = 0;
+  CK(cudaMemcpyAsync(&nc, d_n, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  *n_clusters = nc;
+  if (nc > cap_clusters) return fail(ctx, FE_ERR_CAPACITY, "cluster_offsets too small");
+  std::vector<int> off(nc + 1);
+  CK(cudaMemcpy(off.data(), d_off, (size_t)(nc + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  memcpy(cluster_offsets, off.data(), (size_t)(nc + 1) * sizeof(int));
+  if (off[nc] > cap_indices) return fail(ctx, FE_ERR_CAPACITY, "indices too small");
+  if (off[nc] > 0 && indices) CK(cudaMemcpy(indices, d_idx, (size_t)off[nc] * sizeof(int), cudaMemcpyDeviceToHost));
+  return FE_OK;
+}
+
+static int stage_keypoints(fe_ctx* ctx, const fe_point_t* cloud, int64_t n, bool singleRing, bool merge,
+                           fe_point_t* kp, int64_t capKp, int64_t* nKp, fe_point_t* kc, int64_t capKc, int64_t* nKc) {
+  if (nKp) *nKp = 0;
+  if (nKc) *nKc = 0;
+  if (n == 0) return FE_OK;
+  Slot& s = ctx->slot[0];
+  int st = ensure_slot(ctx, s, true);
+  if (st) return st;
+  st = ensure_kc(ctx, s);
+  if (st) return st;
+  int nch;
+  st = stage_upload_k1(ctx, s, cloud, n, singleRing ? 0 : F_RING, &nch);
+  if (st) return st;
+  CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), s.stream));
+  k_cluster_rings<<<1, NT2, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, ctx->dp,
+                                                      singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, s.d_kcPool,
+                                                      s.capKc, s.d_kcBase, s.d_kcCnt, s.d_ctr);
+  ctx->launches++;
+  if (merge) {
+    k_merge_keypoints<<<1, NT2, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, ctx->dp, s.d_kpPool, (int)s.capKp,
+                                                          s.d_kpBase, s.d_kpCnt, nullptr, nullptr, s.d_ctr);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
+  std::vector<int64_t> off;
+  std::vector<fe_point_t> pts;
+  if (merge) {
+    int base = 0, cnt = 0;
+    CK(cudaMemcpy(&base, s.d_kpBase, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&cnt, s.d_kpCnt, sizeof(int), cudaMemcpyDeviceToHost));
+    pts.resize(cnt);
+    if (cnt) CK(cudaMemcpy(pts.data(), s.d_kpPool + base, (size_t)cnt * sizeof(float4), cudaMemcpyDeviceToHost));
+  } else {
+    st = gather_to_host(ctx, s, 1, false, s.d_kfPool, s.d_kfCnt, s.d_kfBase, off, pts);
+    if (st) return st;
+  }
+  st = copy_points_out(ctx, pts, kp, capKp, nKp);
+  if (st) return st;
+  st = gather_to_host(ctx, s, 1, false, s.d_kcPool, s.d_kcCnt, s.d_kcBase, off, pts);
+  if (st) return st;
+  return copy_points_out(ctx, pts, kc, capKc, nKc);
+}
+
+int fe_get_cylinder_segments(fe_ctx_t* ctx, const fe_point_t* ring_cloud, int64_t n, fe_point_t* centroids,
+                             int64_t cap_centroids, int64_t* n_centroids, fe_point_t* cluster_cloud,
+                             int64_t cap_cloud, int64_t* n_cloud) {
+  if (!ctx || n < 0 || (n > 0 && !ring_cloud)) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return stage_keypoints(ctx, ring_cloud, n, true, false, centroids, cap_centroids, n_centroids, cluster_cloud, cap_cloud, n_cloud);
+}
+
+int fe_estimate_keypoints(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, fe_point_t* keypoints,
+                          int64_t cap_keypoints, int64_t* n_keypoints, fe_point_t* keypoint_cloud,
+                          int64_t cap_cloud, int64_t* n_cloud) {
+  if (!ctx || n < 0 || (n > 0 && !cloud)) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return stage_keypoints(ctx, cloud, n, false, true, keypoints, cap_keypoints, n_keypoints, keypoint_cloud, cap_cloud, n_cloud);
+}
+
+int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t n, const fe_point_t* keypoints,
+                            int64_t k, float* descriptors) {
+  if (!ctx || n < 0 || k < 0 || (n > 0 && !cloud_full) || (k > 0 && (!keypoints || !descriptors))) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (k == 0) return FE_OK;  // src:331-332
+  Slot& s = ctx->slot[0];
+  int st = ensure_slot(ctx, s, true);
+  if (st) return st;
+  if (k > s.capKp) return fail(ctx, FE_ERR_CAPACITY, "more keypoints than max_keypoints_per_call");
+  // the search surface only matters around the keypoints: grid over their bounding box
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = 0; i < k; i++) {
+    const float v[3] = {keypoints[i].x, keypoints[i].y, keypoints[i].z};
+    if (!std::isfinite(v[0]) || !std::isfinite(v[1]) || !std::isfinite(v[2])) continue;
+    for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], v[d]); hi[d] = std::max(hi[d], v[d]); }
+  }
+  if (!(lo[0] <= hi[0])) { for (int d = 0; d < 3; d++) { lo[d] = 0.f; hi[d] = 0.f; } }
+  DevParams saved = ctx->dp;
+  surface_grid(ctx->dp, ctx->params.descriptor_radius, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+  DevParams P = ctx->dp;
+  auto restore = [&](int code) { ctx->dp = saved; return code; };
+  int nch = 0;
+  st = stage_upload_k1(ctx, s, cloud_full, n, F_SURF, &nch);
+  if (st) return restore(st);
+  if (n == 0) {  // one empty scan
+    int64_t offs[2] = {0, 0}; int64_t np0;
+    st = stage_scans(ctx, s, offs, nullptr, 1, &np0, &nch);
+    if (st) return restore(st);
+  }
+  st = ensure_rowstart(ctx, s, 1);
+  if (st) return restore(st);
+  cudaStream_t q = s.stream;
+  std::vector<int> kpOff = {0, (int)k};
+  std::vector<int> kpScan((size_t)k, 0);
+  if (cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), q) != cudaSuccess ||
+      cudaMemcpyAsync(s.d_kpOff, kpOff.data(), 2 * sizeof(int), cudaMemcpyHostToDevice, q) != cudaSuccess ||
+      cudaMemcpyAsync(s.d_kpScan, kpScan.data(), (size_t)k * sizeof(int), cudaMemcpyHostToDevice, q) != cudaSuccess ||
+      cudaMemcpyAsync(s.d_kpOut, keypoints, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, q) != cudaSuccess ||
+      cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(int), q) != cudaSuccess)
+    return restore(fail(ctx, FE_ERR_CUDA, "staging of the descriptor inputs failed"));
+  k_surface_grid<<<1, NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
+                                   s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr);
+  k_desc_mark<<<148 * 4, 256, 0, q>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, 1, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P,
+                                      s.d_rho, s.d_kpNbr);
+  if (n > 0) {
+    k_density<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 64), 256, 0, q>>>(s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P,
+                                                                               (long long)n, s.d_rho);
+    ctx->launches++;
+  }
+  k_desc_hist<<<148 * 4, 256, 0, q>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, 1, s.d_kpNbr, s.d_sorted, s.d_sortedKey, s.d_rowStart,
+                                      s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_desc, s.d_ctr);
+  ctx->launches += 3;
+  ctx->dp = saved;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, q));
+  CK(cudaMemcpyAsync(descriptors, s.d_desc, (size_t)k * FE_DESC_LEN * sizeof(float), cudaMemcpyDeviceToHost, q));
+  CK(cudaStreamSynchronize(q));
+  if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
+  return FE_OK;
+}
+
+int fe_pack_point_descriptors(const fe_point_t* keypoints, const float* descriptors, int64_t k, float* records) {
+  if (k < 0 || (k > 0 && (!keypoints || !descriptors || !records))) return FE_ERR_INVALID;
+  for (int64_t i = 0; i < k; i++) {
+    float* r = records + i * FE_RECORD_FLOATS;
+    memset(r, 0, FE_RECORD_FLOATS * sizeof(float));
+    // PCL_ADD_POINT4D: x,y,z + one pad float (not a registered field: stays value-initialised 0)
+    r[0] = keypoints[i].x; r[1] = keypoints[i].y; r[2] = keypoints[i].z;
+    r[4] = keypoints[i].intensity;
+    memcpy(r + 5, descriptors + i * FE_DESC_LEN, FE_DESC_LEN * sizeof(float));
+    // rf[9] at r + 5 + 1980 stays zero (3dsc.hpp zeroes it); 2 floats of tail padding (EIGEN_ALIGN16)
+  }
+  return FE_OK;
+}
+
+// debug / test hook: the cluster order PCL's final std::sort leaves, from the replay the kernels use
+void fe_debug_sort_replay(const int32_t* sizes, int32_t n, int32_t* order_out) {
+  std::vector<int> ids(n);
+  for (int i = 0; i < n; i++) ids[i] = i;
+  fe::pcl_cluster_order(ids.data(), n, [=](int id) { return sizes[id]; });
+  for (int i = 0; i < n; i++) order_out[i] = ids[i];
+}
+
+}  // extern "C"

@@ -1,0 +1,1089 @@
+// fe_kernels.cuh — the sm_100a kernels of the per-scan keypoint pipeline.
+//
+//   K1  k_level_crop_ring     getElevationAngles + rotateCloud + filterCloud + ring bucketing
+//                             (reference src:147-183, 200-202), fused, one pass over the points
+//   K2  k_cluster_rings       per-ring EuclideanClusterExtraction + getCylinderSegments gating
+//                             (src:261-327): uniform grid (cell = tolerance) built by a block
+//                             radix sort of cell keys in shared memory, atomic union-find over
+//                             the neighbour cells, segmented per-cluster reductions
+//   K3  k_merge_keypoints     cross-ring merge of ring centroids (src:205-257)
+//   K4a k_surface_grid        2-D cell sort of the descriptor search surface (cell >= R/5)
+//   K4b k_desc_mark           which surface points are inside some keypoint's sphere
+//   K4c k_density             3DSC local point density, once per marked point
+//   K4d k_desc_hist           1980-bin shape context per keypoint, shared-memory histogram
+//
+// Batched over scans: every kernel addresses scan s through CSR offsets; blocks never cross scans.
+#pragma once
+#include <math.h>
+#include "fe_device.cuh"
+#include "sort_replay.h"
+#include "../../include/fe_b200.h"
+
+namespace fe {
+
+constexpr int CH = 2048;        // points per K1 chunk (one block)
+constexpr int MAXCHUNK = 1024;  // chunks per scan the per-scan kernels can index (2M points)
+constexpr int NT2 = 512;        // threads of the per-scan clustering / grid kernels
+constexpr int ECAP = 2944;      // cluster entries a block holds in shared memory at once
+
+// error bits reported through DevCounters::err
+enum {
+  ERR_RING_CAP = 1,   // one ring of one scan has more entries than ECAP
+  ERR_KF_POOL = 2,    // ring-centroid pool exhausted
+  ERR_KP_POOL = 4,    // keypoint pool exhausted
+  ERR_MERGE_CAP = 8,  // a scan has more ring centroids than ECAP
+  ERR_AXIS_CAP = 16,  // more keypoints in one scan than precomputed 3DSC axes
+  ERR_CHUNKS = 32,    // scan has more than MAXCHUNK chunks
+  ERR_KC_POOL = 64    // keypoint_cloud pool exhausted
+};
+
+// K1 flags
+enum { F_ELEV = 1, F_ROT = 2, F_CROP = 4, F_RING = 8, F_SURF = 16 };
+
+struct DevParams {
+  // filterCloud limits as pcl::PassThrough stores them (float)
+  float xmin, xmax, ymin, ymax, zmin, zmax;
+  // descriptor search surface: keep box and 2-D grid (origin sx0,sy0; cell 1/sg_inv)
+  float sx0, sx1, sy0, sy1, sz0, sz1;
+  float sg_inv;
+  int sg_nx, sg_ny, sg_bx;  // key = (cy << sg_bx) | cx
+  // ring clustering
+  float tol_f, r2f_cluster;
+  int min_count, max_count;
+  double two_radius_threshold;  // 2*clusterRadiusThreshold (src:316)
+  double radius_threshold;      // clusterRadiusThreshold (src:217)
+  // merge
+  float merge_tol_f, r2f_merge;
+  int min_channels;
+  // 3DSC
+  float R2f, rho2f, Rpad, rhopad;
+  float radii[16], theta[12], phi[13];
+  int estimate_descriptors;
+};
+
+struct DevCounters {
+  int kf_cursor;   // ring-centroid pool
+  int kp_cursor;   // keypoint pool
+  int kc_cursor;   // keypoint_cloud pool
+  int err;
+  int kp_total;
+  int pad[3];
+};
+
+// ============================================================================================
+// K1 — fused elevation / level / crop / ring-bucket, order-preserving compaction per chunk.
+// Block = one chunk of CH consecutive points of one scan; 256 threads; warp w owns points
+// [256w, 256w+256) of the chunk in 8 coalesced rounds (float4 loads).  Survivors are written to
+// the chunk's own slot of the output arrays (same CSR as the input) with their counts, so the
+// per-scan consumers concatenate pieces in order and no global prefix sum is needed.
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_level_crop_ring(
+    const float4* __restrict__ pts, const long long* __restrict__ scan_off,
+    const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
+    int flags, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
+    unsigned* __restrict__ cropMeta, int* __restrict__ cropCnt, float4* __restrict__ full_out) {
+  __shared__ int s_scan;
+  __shared__ int s_ws[8], s_wc[8];
+  const int chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) {
+    int lo = 0, hi = n_scans - 1;  // largest s with chunk_off[s] <= chunk
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (chunk_off[mid] <= chunk) lo = mid; else hi = mid - 1;
+    }
+    s_scan = lo;
+  }
+  __syncthreads();
+  const int s = s_scan;
+  const int c = chunk - chunk_off[s];
+  const long long base = scan_off[s] + (long long)c * CH;
+  const int nIn = (int)min((long long)CH, scan_off[s + 1] - base);
+  float m[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) m[i] = (flags & F_ROT) ? rot[s * 9 + i] : 0.0f;
+
+  float4 o[8];
+  unsigned code = 0;             // 8 x 4 bits: ring id of round r (first ring containing el)
+  unsigned fl = 0;               // bit r: surf, bit 8+r: crop, bit 16+r: dual ring, bit 24+r: no ring
+  unsigned ms[8], mc[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int j = w * 256 + r * 32 + lane;
+    bool fs = false, fc = false;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < nIn) {
+      const float4 p = __ldg(pts + base + j);
+      float el = p.w;
+      if (flags & F_ELEV) {
+        // getElevationAngles, src:147-156 — double throughout
+        const double x = p.x, y = p.y, z = p.z;
+        const double az = atan2(y, x);
+        double sn, cs;
+        sincos(az, &sn, &cs);
+        const double xp = __dadd_rn(__dmul_rn(cs, x), __dmul_rn(sn, y));
+        const double eld = __ddiv_rn(__dmul_rn(atan2(z, xp), 180.0), 3.14159265358979323846);
+        el = (float)eld;
+      }
+      if (flags & F_ROT) {
+        // pcl::transformPointCloud, PCL 1.8.0 scalar form: left to right, unfused, + translation 0
+        q.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], p.x), __fmul_rn(m[1], p.y)), __fmul_rn(m[2], p.z)), 0.0f);
+        q.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[3], p.x), __fmul_rn(m[4], p.y)), __fmul_rn(m[5], p.z)), 0.0f);
+        q.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[6], p.x), __fmul_rn(m[7], p.y)), __fmul_rn(m[8], p.z)), 0.0f);
+      } else {
+        q.x = p.x; q.y = p.y; q.z = p.z;
+      }
+      q.w = el;
+      if (full_out) full_out[base + j] = q;
+      const bool fin = finite3(q.x, q.y, q.z);
+      // pcl::PassThrough: non-finite dropped, inclusive float limits (src:169-183)
+      fc = fin;
+      if (flags & F_CROP)
+        fc = fin && !(q.z < P.zmin || q.z > P.zmax) && !(q.y < P.ymin || q.y > P.ymax) &&
+             !(q.x < P.xmin || q.x > P.xmax);
+      if (fc) {
+        unsigned rm = 1u;
+        if (flags & F_RING) {
+          // ring i keeps (i-7)*2-1 +- 1 inclusive (src:200-202); windows share their end points
+          rm = 0u;
+          if (isfinite(el)) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const float lo = (float)(2 * i - 16), hi = (float)(2 * i - 14);
+              if (!(el < lo || el > hi)) rm |= 1u << i;
+            }
+          }
+        }
+        if (rm == 0u) fl |= 1u << (24 + r);
+        else {
+          code |= (unsigned)(__ffs(rm) - 1) << (4 * r);
+          if (__popc(rm) > 1) fl |= 1u << (16 + r);
+        }
+      }
+      if (flags & F_SURF)
+        fs = fin && q.x >= P.sx0 && q.x <= P.sx1 && q.y >= P.sy0 && q.y <= P.sy1 && q.z >= P.sz0 && q.z <= P.sz1;
+    }
+    o[r] = q;
+    if (fs) fl |= 1u << r;
+    if (fc) fl |= 1u << (8 + r);
+    ms[r] = __ballot_sync(FE_FULL, fs);
+    mc[r] = __ballot_sync(FE_FULL, fc);
+  }
+  int ts = 0, tc = 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) { ts += __popc(ms[r]); tc += __popc(mc[r]); }
+  if (lane == 0) { s_ws[w] = ts; s_wc[w] = tc; }
+  __syncthreads();
+  int os = 0, oc = 0, tots = 0, totc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (i < w) { os += s_ws[i]; oc += s_wc[i]; }
+    tots += s_ws[i]; totc += s_wc[i];
+  }
+  if (tid == 0) {
+    if (surfCnt) surfCnt[chunk] = tots;
+    if (cropCnt) cropCnt[chunk] = totc;
+  }
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (fl & (1u << r)) surf[base + os + __popc(ms[r] & lt)] = o[r];
+    if (fl & (1u << (8 + r))) {
+      const long long d = base + oc + __popc(mc[r] & lt);
+      crop[d] = o[r];
+      unsigned cd = (code >> (4 * r)) & 15u;
+      if (fl & (1u << (16 + r))) cd |= 16u;
+      if (fl & (1u << (24 + r))) cd = 32u;
+      const unsigned idx = (unsigned)(c * CH + w * 256 + r * 32 + lane);
+      cropMeta[d] = (idx << 6) | cd;
+    }
+    os += __popc(ms[r]);
+    oc += __popc(mc[r]);
+  }
+}
+
+// ============================================================================================
+// Shared-memory workspace of the per-scan clustering kernels.
+// ============================================================================================
+struct ClusterSm {
+  float *x, *y, *z;
+  unsigned* gref;          // where the entry lives in the global array it came from
+  unsigned char* ring;
+  unsigned *keyA, *keyB;
+  unsigned short *valA, *valB, *aux, *lst;
+  unsigned short* wc;      // NT2/32 * 257
+  unsigned* base;          // 256 + 32
+  int* misc;               // MISC_INTS
+};
+constexpr int MISC_INTS = MAXCHUNK + 1 + 128;
+constexpr size_t cluster_smem_bytes() {
+  return (size_t)ECAP * (12 + 4 + 1 + 8 + 8) + (NT2 / 32) * 257 * 2 + (256 + 32) * 4 + MISC_INTS * 4 + 64;
+}
+
+__device__ __forceinline__ void cluster_sm_carve(unsigned char* p, ClusterSm& S) {
+  S.x = (float*)p; p += ECAP * 4;
+  S.y = (float*)p; p += ECAP * 4;
+  S.z = (float*)p; p += ECAP * 4;
+  S.gref = (unsigned*)p; p += ECAP * 4;
+  S.keyA = (unsigned*)p; p += ECAP * 4;
+  S.keyB = (unsigned*)p; p += ECAP * 4;
+  S.base = (unsigned*)p; p += (256 + 32) * 4;
+  S.misc = (int*)p; p += MISC_INTS * 4;
+  S.valA = (unsigned short*)p; p += ECAP * 2;
+  S.valB = (unsigned short*)p; p += ECAP * 2;
+  S.aux = (unsigned short*)p; p += ECAP * 2;
+  S.lst = (unsigned short*)p; p += ECAP * 2;
+  S.wc = (unsigned short*)p; p += (NT2 / 32) * 257 * 2;
+  S.ring = (unsigned char*)p;
+}
+
+struct ClusterOut {
+  int nC;                  // clusters that passed the size gate, in PCL's output order
+  unsigned short* slotRoot;   // [nC] entry index of the cluster's first (smallest) member
+  unsigned* cnt;              // [E] cnt[root] = cluster size
+  unsigned short* mem;        // [sum of sizes] members, cluster after cluster, ascending
+  unsigned short* slotStart;  // [nC] offset of each cluster in mem
+  unsigned* parent;           // [E] root of every entry
+};
+
+// pcl::EuclideanClusterExtraction::extract (PCL 1.8.0 extract_clusters.hpp) over the E entries
+// held in S (x,y,z,ring), ring by ring: connected components of {d2 < r2f}, size gate applied
+// to whole components, members ascending, clusters in discovery order then reordered by the
+// std::sort(rbegin, rend, size<) replay.  Entries must be in the original point order.
+// misc[96..127] is scratch.
+template <int NT>
+__device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int minSz, int maxSz,
+                                int nRings, ClusterOut& out) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int* sc = S.misc + MAXCHUNK + 1;        // 128 ints of scratch
+  float* bb = (float*)(sc + 40);          // 6 floats
+  // ---- bounding box of the entries (grid origin) ----
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int e = tid; e < E; e += NT) {
+    mn[0] = fminf(mn[0], S.x[e]); mx[0] = fmaxf(mx[0], S.x[e]);
+    mn[1] = fminf(mn[1], S.y[e]); mx[1] = fmaxf(mx[1], S.y[e]);
+    mn[2] = fminf(mn[2], S.z[e]); mx[2] = fmaxf(mx[2], S.z[e]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(FE_FULL, mn[k], d));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(FE_FULL, mx[k], d));
+    }
+  float* red = (float*)(sc + 48);  // NT/32 * 6 floats <= 96 -> use S.wc area instead (free here)
+  red = (float*)S.wc;
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { red[w * 6 + k] = mn[k]; red[w * 6 + 3 + k] = mx[k]; }
+  }
+  __syncthreads();
+  if (tid < 6) {
+    float v = red[tid];
+    for (int i = 1; i < NT / 32; i++) v = (tid < 3) ? fminf(v, red[i * 6 + tid]) : fmaxf(v, red[i * 6 + tid]);
+    bb[tid] = v;
+  }
+  __syncthreads();
+  // cell slightly larger than the tolerance so that linked points are always in adjacent cells
+  // despite the rounding of the cell computation; indices clamp (monotone map keeps adjacency)
+  const float inv = 1.0f / (tol_f * 1.002f);
+  const float ox = bb[0], oy = bb[1], oz = bb[2];
+  const int nx = min(1024, (int)fminf(1023.0f, floorf((bb[3] - ox) * inv)) + 1);
+  const int ny = min(1024, (int)fminf(1023.0f, floorf((bb[4] - oy) * inv)) + 1);
+  const int nz = min(256, (int)fminf(255.0f, floorf((bb[5] - oz) * inv)) + 1);
+  const int bx = bits_for(nx - 1), by = bits_for(ny - 1), bz = bits_for(nz - 1);
+  const int br = bits_for(nRings - 1);
+  const int keybits = bx + by + bz + br;
+  // ---- keys ----
+  for (int e = tid; e < E; e += NT) {
+    int cx = (int)floorf((S.x[e] - ox) * inv), cy = (int)floorf((S.y[e] - oy) * inv), cz = (int)floorf((S.z[e] - oz) * inv);
+    cx = max(0, min(cx, nx - 1)); cy = max(0, min(cy, ny - 1)); cz = max(0, min(cz, nz - 1));
+    S.keyA[e] = ((((unsigned)S.ring[e] << bz | (unsigned)cz) << by | (unsigned)cy) << bx) | (unsigned)cx;
+    S.valA[e] = (unsigned short)e;
+  }
+  // ---- radix sort of (key, entry) ----
+  unsigned *kS = S.keyA, *kT = S.keyB;
+  unsigned short *vS = S.valA, *vT = S.valB;
+  for (int shift = 0; shift < keybits; shift += 8) {
+    unsigned* ki = kS; unsigned* ko = kT; unsigned short* vi = vS; unsigned short* vo = vT;
+    block_radix_pass<NT, unsigned short>(
+        E, [=](int i) { return (ki[i] >> shift) & 255u; },
+        [=](int i, int pos) { ko[pos] = ki[i]; vo[pos] = vi[i]; }, S.wc, S.base);
+    kS = ko; kT = ki; vS = vo; vT = vi;
+  }
+  __syncthreads();
+  // ---- union-find over the neighbour cells ----
+  unsigned* parent = kT;
+  for (int e = tid; e < E; e += NT) parent[e] = (unsigned)e;
+  __syncthreads();
+  const unsigned mxm = (1u << bx) - 1u, mym = (1u << by) - 1u, mzm = (1u << bz) - 1u;
+  for (int p = tid; p < E; p += NT) {
+    const unsigned key = kS[p];
+    const unsigned e = vS[p];
+    const int cx = (int)(key & mxm), cy = (int)((key >> bx) & mym), cz = (int)((key >> (bx + by)) & mzm);
+    const unsigned rg = key >> (bx + by + bz);
+    const float px = S.x[e], py = S.y[e], pz = S.z[e];
+    for (int dz = -1; dz <= 0; dz++) {
+      const int zz = cz + dz;
+      if (zz < 0) continue;
+      const int dyhi = (dz == 0) ? 0 : 1;
+      for (int dy = -1; dy <= dyhi; dy++) {
+        const int yy = cy + dy;
+        if (yy < 0 || yy >= ny) continue;
+        const unsigned rowk = (((rg << bz) | (unsigned)zz) << by | (unsigned)yy) << bx;
+        const unsigned klo = rowk | (unsigned)max(cx - 1, 0);
+        const unsigned khi = rowk | (unsigned)min(cx + 1, nx - 1);
+        const bool own = (dz == 0 && dy == 0);
+        int lo = 0, hi = own ? p : E;  // lower_bound(klo) in kS[0, hi)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (kS[mid] < klo) lo = mid + 1; else hi = mid;
+        }
+        const int end = own ? p : E;
+        for (int q = lo; q < end; q++) {
+          if (kS[q] > khi) break;
+          const unsigned e2 = vS[q];
+          const float d2 = l2_simple(px, py, pz, S.x[e2], S.y[e2], S.z[e2]);
+          if (d2 < r2f) uf_union(parent, e, e2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- flatten, component sizes ----
+  unsigned* cnt = kS;
+  for (int e = tid; e < E; e += NT) { parent[e] = uf_find(parent, (unsigned)e); cnt[e] = 0; }
+  __syncthreads();
+  for (int e = tid; e < E; e += NT) atomicAdd(&cnt[parent[e]], 1u);
+  __syncthreads();
+  // ---- size-gated roots in discovery order (ascending first member) ----
+  int nC = 0;
+  {
+    int run = 0;
+    for (int e0 = 0; e0 < E; e0 += NT) {
+      const int e = e0 + tid;
+      const int keep = (e < E && parent[e] == (unsigned)e && (int)cnt[e] >= minSz && (int)cnt[e] <= maxSz) ? 1 : 0;
+      int tot;
+      const int pos = block_excl_scan<NT>(keep, &tot, sc);
+      if (keep) vT[run + pos] = (unsigned short)e;
+      run += tot;
+    }
+    nC = run;
+  }
+  __syncthreads();
+  out.nC = nC;
+  out.cnt = cnt;
+  out.parent = parent;
+  out.slotRoot = S.lst;
+  if (nC == 0) { out.mem = vS; out.slotStart = S.aux; return; }
+  // ---- split by ring (stable), then PCL's final cluster order inside every ring ----
+  int* ringEnd = sc + 64;  // 16 ints
+  if (nRings > 1) {
+    unsigned short* src = vT; unsigned short* dst = S.lst; unsigned char* rng = S.ring;
+    block_radix_pass<NT, unsigned short>(
+        nC, [=](int i) { return (unsigned)rng[src[i]]; }, [=](int i, int pos) { dst[pos] = src[i]; }, S.wc, S.base);
+    if (tid < 16) ringEnd[tid] = (int)S.base[tid];
+  } else {
+    for (int i = tid; i < nC; i += NT) S.lst[i] = vT[i];
+    if (tid < 16) ringEnd[tid] = nC;
+  }
+  __syncthreads();
+  if (lane == 0 && w < nRings) {
+    const int b = (w == 0) ? 0 : ringEnd[w - 1];
+    const int n = ringEnd[w] - b;
+    if (n > 1) {
+      const unsigned* c2 = cnt;
+      pcl_cluster_order(S.lst + b, n, [=](unsigned short id) { return c2[id]; });
+    }
+  }
+  if (nRings > NT / 32 && tid == 0) {  // not reachable with 16 rings and 16 warps; kept for safety
+    for (int r = NT / 32; r < nRings; r++) {
+      const int b = ringEnd[r - 1];
+      const int n = ringEnd[r] - b;
+      const unsigned* c2 = cnt;
+      if (n > 1) pcl_cluster_order(S.lst + b, n, [=](unsigned short id) { return c2[id]; });
+    }
+  }
+  for (int e = tid; e < E; e += NT) S.aux[e] = 0xFFFFu;
+  __syncthreads();
+  for (int i = tid; i < nC; i += NT) S.aux[S.lst[i]] = (unsigned short)i;
+  __syncthreads();
+  // ---- member lists: stable sort of the entries by cluster slot (ascending entry inside) ----
+  {
+    const int kb = bits_for(nC);  // values 0..nC (nC = not in a kept cluster)
+    unsigned short* aux = S.aux;
+    const unsigned* par = parent;
+    const unsigned nCu = (unsigned)nC;
+    unsigned short* o1 = vS;
+    block_radix_pass<NT, unsigned short>(
+        E, [=](int i) { unsigned s = aux[par[i]]; if (s == 0xFFFFu) s = nCu; return s & 255u; },
+        [=](int i, int pos) { o1[pos] = (unsigned short)i; }, S.wc, S.base);
+    out.mem = vS;
+    if (kb > 8) {
+      unsigned short* o2 = vT;
+      block_radix_pass<NT, unsigned short>(
+          E, [=](int i) { unsigned s = aux[par[o1[i]]]; if (s == 0xFFFFu) s = nCu; return (s >> 8) & 255u; },
+          [=](int i, int pos) { o2[pos] = o1[i]; }, S.wc, S.base);
+      out.mem = vT;
+    }
+  }
+  __syncthreads();
+  // ---- slot offsets ----
+  {
+    int run = 0;
+    for (int i0 = 0; i0 < nC; i0 += NT) {
+      const int i = i0 + tid;
+      const int v = (i < nC) ? (int)cnt[S.lst[i]] : 0;
+      int tot;
+      const int pos = block_excl_scan<NT>(v, &tot, sc);
+      if (i < nC) S.aux[i] = (unsigned short)(run + pos);
+      run += tot;
+    }
+  }
+  out.slotStart = S.aux;
+  __syncthreads();
+}
+
+// Prefix of a scan's chunk counts into misc[0..nch]; returns the total.  All threads call.
+template <int NT>
+__device__ int chunk_prefix(const int* __restrict__ cnt, int nch, int* pre, int* sc) {
+  int run = 0;
+  for (int c0 = 0; c0 < nch; c0 += NT) {
+    const int c = c0 + threadIdx.x;
+    const int v = (c < nch) ? cnt[c] : 0;
+    int tot;
+    const int pos = block_excl_scan<NT>(v, &tot, sc);
+    if (c < nch) pre[c] = run + pos;
+    run += tot;
+  }
+  if (threadIdx.x == 0) pre[nch] = run;
+  __syncthreads();
+  return run;
+}
+
+// position in the piece-wise array of the i-th survivor of a scan
+__device__ __forceinline__ long long piece_pos(const int* pre, int nch, int i, long long base) {
+  int lo = 0, hi = nch - 1;  // largest c with pre[c] <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (pre[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  return base + (long long)lo * CH + (i - pre[lo]);
+}
+
+// ============================================================================================
+// K2 — per-ring clustering and getCylinderSegments gating for one scan per block.
+// ============================================================================================
+__global__ void __launch_bounds__(NT2, 2) k_cluster_rings(
+    const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta,
+    const int* __restrict__ cropCnt, const long long* __restrict__ scan_off,
+    const int* __restrict__ chunk_off, DevParams P, int single_ring,
+    float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
+    float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
+    DevCounters* __restrict__ ctr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClusterSm S;
+  cluster_sm_carve(smem_raw, S);
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* pre = S.misc;
+  int* sc = S.misc + MAXCHUNK + 1;
+  int* ringCnt = sc + 80;  // 16
+  const long long base = scan_off[s];
+  const int nch = chunk_off[s + 1] - chunk_off[s];
+  if (tid < 16) { kfBase[s * 16 + tid] = 0; kfCnt[s * 16 + tid] = 0; if (kcBase) { kcBase[s * 16 + tid] = 0; kcCnt[s * 16 + tid] = 0; } }
+  if (nch > MAXCHUNK) { if (tid == 0) atomicOr(&ctr->err, ERR_CHUNKS); return; }
+  const int Nc = chunk_prefix<NT2>(cropCnt + chunk_off[s], nch, pre, sc);
+  if (Nc == 0) return;
+  // entries per ring
+  if (tid < 16) ringCnt[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < Nc; i += NT2) {
+    const unsigned cd = cropMeta[piece_pos(pre, nch, i, base)] & 63u;
+    if (cd & 32u) continue;
+    const int r = single_ring ? 0 : (int)(cd & 15u);
+    atomicAdd(&ringCnt[r], 1);
+    if ((cd & 16u) && !single_ring) atomicAdd(&ringCnt[r + 1], 1);
+  }
+  __syncthreads();
+  const int nRingsAll = single_ring ? 1 : 16;
+  int group = 0;
+  int r0 = 0;
+  while (r0 < nRingsAll) {
+    // greedy run of consecutive rings that fits the shared-memory capacity
+    int r1 = r0, tot = 0;
+    while (r1 < nRingsAll && tot + ringCnt[r1] <= ECAP) { tot += ringCnt[r1]; r1++; }
+    if (r1 == r0) {  // a single ring is larger than the capacity
+      if (tid == 0) atomicOr(&ctr->err, ERR_RING_CAP);
+      return;
+    }
+    if (tot > 0) {
+      // ---- gather the entries of rings [r0, r1) in original order ----
+      int run = 0;
+      for (int i0 = 0; i0 < Nc; i0 += NT2) {
+        const int i = i0 + tid;
+        int take = 0, ra = 0, rb = -1;
+        long long pp = 0;
+        if (i < Nc) {
+          pp = piece_pos(pre, nch, i, base);
+          const unsigned cd = cropMeta[pp] & 63u;
+          if (!(cd & 32u)) {
+            ra = single_ring ? 0 : (int)(cd & 15u);
+            if ((cd & 16u) && !single_ring) rb = ra + 1;
+            const bool ina = (ra >= r0 && ra < r1), inb = (rb >= r0 && rb < r1);
+            if (!ina && inb) { ra = rb; rb = -1; }
+            if (!inb) rb = -1;
+            take = (ina ? 1 : 0) + (inb ? 1 : 0);
+          }
+        }
+        int t2;
+        const int pos = block_excl_scan<NT2>(take, &t2, sc);
+        if (take) {
+          const float4 q = crop[pp];
+          int e = run + pos;
+          S.x[e] = q.x; S.y[e] = q.y; S.z[e] = q.z; S.gref[e] = (unsigned)pp; S.ring[e] = (unsigned char)(ra - r0);
+          if (take == 2) {
+            e++;
+            S.x[e] = q.x; S.y[e] = q.y; S.z[e] = q.z; S.gref[e] = (unsigned)pp; S.ring[e] = (unsigned char)(rb - r0);
+          }
+        }
+        run += t2;
+      }
+      __syncthreads();
+      const int E = run;
+      ClusterOut C;
+      cluster_extract<NT2>(S, E, P.tol_f, P.r2f_cluster, P.min_count, P.max_count, r1 - r0, C);
+      // ---- getCylinderSegments gate + centroid per cluster (src:282-325), one thread each ----
+      int* sh = sc + 100;  // [0] = pool base, [1] = kc base
+      int runG = 0, runM = 0;
+      // pass 1 counts, pass 2 writes; the per-cluster result is cached in registers per tile
+      for (int pass = 0; pass < 2; pass++) {
+        int accG = 0, accM = 0;
+        for (int i0 = 0; i0 < C.nC; i0 += NT2) {
+          const int i = i0 + tid;
+          int ok = 0, size = 0;
+          float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < C.nC) {
+            const unsigned root = C.slotRoot[i];
+            size = (int)C.cnt[root];
+            const int st = C.slotStart[i];
+            double sumx = 0.0, sumy = 0.0, sumz = 0.0;
+            double minx = 1000.0, maxx = -1000.0, miny = 1000.0, maxy = -1000.0;
+            for (int j = 0; j < size; j++) {
+              const int e = C.mem[st + j];
+              const double x = S.x[e], y = S.y[e], z = S.z[e];
+              sumx += x; sumy += y; sumz += z;
+              if (x < minx) minx = x;
+              if (y < miny) miny = y;
+              if (x > maxx) maxx = x;
+              if (y > maxy) maxy = y;
+            }
+            const double ddx = maxx - minx, ddy = maxy - miny;
+            const double diameter = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+            if (diameter < P.two_radius_threshold) {
+              ok = 1;
+              cen.x = (float)(sumx / (double)size);
+              cen.y = (float)(sumy / (double)size);
+              cen.z = (float)(sumz / (double)size);
+              if (pass == 1) cen.w = crop[S.gref[root]].w;  // intensity of indices[0] (src:320)
+            }
+          }
+          int tg, tm;
+          const int pg = block_excl_scan<NT2>(ok, &tg, sc);
+          int pm = 0;
+          if (kcPool) pm = block_excl_scan<NT2>(ok ? size : 0, &tm, sc); else tm = 0;
+          if (pass == 1 && ok) {
+            const int b = sh[0];
+            if (b >= 0) kfPool[b + accG + pg] = cen;
+            if (kcPool && sh[1] >= 0) {
+              const unsigned root = C.slotRoot[i];
+              const int st = C.slotStart[i];
+              (void)root;
+              for (int j = 0; j < size; j++) kcPool[sh[1] + accM + pm + j] = crop[S.gref[C.mem[st + j]]];
+            }
+          }
+          accG += tg; accM += tm;
+        }
+        if (pass == 0) {
+          runG = accG; runM = accM;
+          __syncthreads();
+          if (tid == 0) {
+            int b = -1, bc = -1;
+            if (runG > 0) {
+              b = atomicAdd(&ctr->kf_cursor, runG);
+              if (b + runG > kfCap) { atomicOr(&ctr->err, ERR_KF_POOL); b = -1; }
+            }
+            if (kcPool && runM > 0) {
+              bc = atomicAdd(&ctr->kc_cursor, runM);
+              if (bc + runM > kcCap) { atomicOr(&ctr->err, ERR_KC_POOL); bc = -1; }
+            }
+            sh[0] = b; sh[1] = bc;
+            kfBase[s * 16 + group] = max(b, 0);
+            kfCnt[s * 16 + group] = (b >= 0) ? runG : 0;
+            if (kcBase) { kcBase[s * 16 + group] = max(bc, 0); kcCnt[s * 16 + group] = (bc >= 0) ? runM : 0; }
+          }
+          __syncthreads();
+          if (runG == 0) break;
+        }
+      }
+      __syncthreads();
+      group++;
+    }
+    r0 = r1;
+  }
+}
+
+// ============================================================================================
+// K3 — cross-ring merge (src:205-257) for one scan per block; also the stage kernel behind
+// fe_extract_clusters when `stage` != 0 (then it just reports the clusters of `crop`).
+// ============================================================================================
+__global__ void __launch_bounds__(NT2, 2) k_merge_keypoints(
+    const float4* __restrict__ kfPool, const int* __restrict__ kfBase, const int* __restrict__ kfCnt,
+    DevParams P, float4* __restrict__ kpPool, int kpCap, int* __restrict__ kpBase,
+    int* __restrict__ kpCnt, float4* __restrict__ kfOut, int* __restrict__ kfOutCnt,
+    DevCounters* __restrict__ ctr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClusterSm S;
+  cluster_sm_carve(smem_raw, S);
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* sc = S.misc + MAXCHUNK + 1;
+  int* pre = S.misc;  // 17 prefix entries of the pieces
+  if (tid == 0) {
+    int run = 0;
+    for (int g = 0; g < 16; g++) { pre[g] = run; run += kfCnt[s * 16 + g]; }
+    pre[16] = run;
+    kpBase[s] = 0; kpCnt[s] = 0;
+  }
+  __syncthreads();
+  const int Kf = pre[16];
+  if (kfOutCnt && tid == 0) kfOutCnt[s] = Kf;
+  if (Kf == 0) return;
+  if (Kf > ECAP) { if (tid == 0) atomicOr(&ctr->err, ERR_MERGE_CAP); return; }
+  for (int i = tid; i < Kf; i += NT2) {
+    int g = 0;
+    while (g < 15 && pre[g + 1] <= i) g++;
+    const int src = kfBase[s * 16 + g] + (i - pre[g]);
+    const float4 q = kfPool[src];
+    S.x[i] = q.x; S.y[i] = q.y;
+    // src:217 — z replaced by intensity*0.75*clusterRadiusThreshold/2 (double, narrowed to float)
+    S.z[i] = (float)__ddiv_rn(__dmul_rn(__dmul_rn((double)q.w, 0.75), P.radius_threshold), 2.0);
+    S.gref[i] = (unsigned)src;
+    S.ring[i] = 0;
+    if (kfOut) kfOut[(long long)s * ECAP + i] = q;
+  }
+  __syncthreads();
+  ClusterOut C;
+  cluster_extract<NT2>(S, Kf, P.merge_tol_f, P.r2f_merge, P.min_channels, 16, 1, C);
+  if (C.nC == 0) return;
+  int* sh = sc + 100;
+  if (tid == 0) {
+    int b = atomicAdd(&ctr->kp_cursor, C.nC);
+    if (b + C.nC > kpCap) { atomicOr(&ctr->err, ERR_KP_POOL); b = -1; }
+    sh[0] = b;
+    kpBase[s] = max(b, 0);
+    kpCnt[s] = (b >= 0) ? C.nC : 0;
+  }
+  __syncthreads();
+  const int b = sh[0];
+  if (b < 0) return;
+  for (int i = tid; i < C.nC; i += NT2) {
+    const unsigned root = C.slotRoot[i];
+    const int size = (int)C.cnt[root];
+    const int st = C.slotStart[i];
+    double sumx = 0.0, sumy = 0.0, sumz = 0.0;
+    for (int j = 0; j < size; j++) {
+      const int e = C.mem[st + j];
+      sumx += (double)S.x[e];
+      sumy += (double)S.y[e];
+      sumz += (double)kfPool[S.gref[e]].z;  // the real z, restored at src:231-232
+    }
+    float4 kp;
+    kp.x = (float)(sumx / (double)size);
+    kp.y = (float)(sumy / (double)size);
+    kp.z = (float)(sumz / (double)size);
+    kp.w = kfPool[S.gref[root]].w;  // src:254
+    kpPool[b + i] = kp;
+  }
+}
+
+// Stage kernel: plain EuclideanClusterExtraction of n points (one block), CSR result.
+__global__ void __launch_bounds__(NT2, 2) k_extract_clusters_stage(
+    const float4* __restrict__ pts, int n, float tol_f, float r2f, int minSz, int maxSz,
+    int* __restrict__ offsets, int capClusters, int* __restrict__ indices, int* __restrict__ nOut) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClusterSm S;
+  cluster_sm_carve(smem_raw, S);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += NT2) {
+    const float4 q = pts[i];
+    S.x[i] = q.x; S.y[i] = q.y; S.z[i] = q.z; S.gref[i] = (unsigned)i; S.ring[i] = 0;
+  }
+  __syncthreads();
+  ClusterOut C;
+  cluster_extract<NT2>(S, n, tol_f, r2f, minSz, maxSz, 1, C);
+  if (tid == 0) { nOut[0] = C.nC; offsets[0] = 0; }
+  if (C.nC > capClusters) return;
+  for (int i = tid; i < C.nC; i += NT2) {
+    const int size = (int)C.cnt[C.slotRoot[i]];
+    const int st = C.slotStart[i];
+    offsets[i + 1] = st + size;
+    for (int j = 0; j < size; j++) indices[st + j] = (int)C.mem[st + j];
+  }
+}
+
+// ============================================================================================
+// Keypoint CSR offsets (one block) and ordered copy of the keypoints out of the pool.
+// ============================================================================================
+__global__ void __launch_bounds__(1024) k_kp_offsets(const int* __restrict__ kpCnt, int n_scans,
+                                                      int* __restrict__ kpOff, DevCounters* ctr) {
+  __shared__ int sc[40];
+  int run = 0;
+  for (int s0 = 0; s0 < n_scans; s0 += 1024) {
+    const int s = s0 + threadIdx.x;
+    const int v = (s < n_scans) ? kpCnt[s] : 0;
+    int tot;
+    const int pos = block_excl_scan<1024>(v, &tot, sc);
+    if (s < n_scans) kpOff[s] = run + pos;
+    run += tot;
+  }
+  if (threadIdx.x == 0) { kpOff[n_scans] = run; ctr->kp_total = run; }
+}
+
+__device__ __forceinline__ int scan_of_keypoint(const int* __restrict__ kpOff, int n_scans, int g) {
+  int lo = 0, hi = n_scans - 1;  // largest s with kpOff[s] <= g
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (kpOff[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void k_kp_gather(const float4* __restrict__ kpPool, const int* __restrict__ kpBase,
+                            const int* __restrict__ kpOff, int n_scans, float4* __restrict__ kpOut,
+                            int* __restrict__ kpScan) {
+  const int total = kpOff[n_scans];
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int s = scan_of_keypoint(kpOff, n_scans, g);
+    kpOut[g] = kpPool[kpBase[s] + (g - kpOff[s])];
+    kpScan[g] = s;
+  }
+}
+
+// Concatenate chunk pieces (or pool pieces) of every scan into a dense CSR array.
+__global__ void k_piece_counts(const int* __restrict__ cnt, const int* __restrict__ chunk_off,
+                               int n_scans, int* __restrict__ perScan) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  int t = 0;
+  for (int c = chunk_off[s]; c < chunk_off[s + 1]; c++) t += cnt[c];
+  perScan[s] = t;
+}
+
+__global__ void __launch_bounds__(256) k_gather_chunks(
+    const float4* __restrict__ src, const int* __restrict__ cnt, const long long* __restrict__ scan_off,
+    const int* __restrict__ chunk_off, const int* __restrict__ outOff, float4* __restrict__ dst) {
+  // one block per scan; chunk after chunk
+  const int s = blockIdx.x;
+  long long o = outOff[s];
+  const long long base = scan_off[s];
+  const int c0 = chunk_off[s], c1 = chunk_off[s + 1];
+  for (int c = c0; c < c1; c++) {
+    const int n = cnt[c];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) dst[o + j] = src[base + (long long)(c - c0) * CH + j];
+    o += n;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gather_pool16(
+    const float4* __restrict__ pool, const int* __restrict__ pBase, const int* __restrict__ pCnt,
+    const int* __restrict__ outOff, float4* __restrict__ dst) {
+  const int s = blockIdx.x;
+  long long o = outOff[s];
+  for (int g = 0; g < 16; g++) {
+    const int n = pCnt[s * 16 + g], b = pBase[s * 16 + g];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) dst[o + j] = pool[b + j];
+    o += n;
+  }
+}
+
+__global__ void k_pool16_counts(const int* __restrict__ pCnt, int n_scans, int* __restrict__ perScan) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  int t = 0;
+  for (int g = 0; g < 16; g++) t += pCnt[s * 16 + g];
+  perScan[s] = t;
+}
+
+// ============================================================================================
+// K4a — 2-D cell grid of the descriptor search surface, one scan per block: radix sort of
+// (cell key, source position) through global memory (L2-resident: a scan is a few hundred KB),
+// then the sorted point array, its key array and a per-row start table.
+// ============================================================================================
+__device__ __forceinline__ int surf_cell(float v, float o, float inv, int n) {
+  int c = (int)floorf((v - o) * inv);
+  return max(0, min(c, n - 1));
+}
+
+__global__ void __launch_bounds__(NT2, 2) k_surface_grid(
+    const float4* __restrict__ surf, const int* __restrict__ surfCnt,
+    const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
+    unsigned* __restrict__ keyA, unsigned* __restrict__ keyB, unsigned* __restrict__ valA,
+    unsigned* __restrict__ valB, float4* __restrict__ sorted, unsigned* __restrict__ sortedKey,
+    int* __restrict__ rowStart, int* __restrict__ surfN, DevCounters* __restrict__ ctr) {
+  __shared__ int pre[MAXCHUNK + 1];
+  __shared__ int sc[40];
+  __shared__ unsigned wc[(NT2 / 32) * 257];
+  __shared__ unsigned rbase[256 + 32];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const long long base = scan_off[s];
+  const int nch = chunk_off[s + 1] - chunk_off[s];
+  int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+  if (nch > MAXCHUNK) { if (tid == 0) { atomicOr(&ctr->err, ERR_CHUNKS); surfN[s] = 0; } return; }
+  const int n = chunk_prefix<NT2>(surfCnt + chunk_off[s], nch, pre, sc);
+  if (tid == 0) surfN[s] = n;
+  if (n == 0) {
+    for (int r = tid; r <= P.sg_ny; r += NT2) rs[r] = 0;
+    return;
+  }
+  unsigned* kA = keyA + base; unsigned* kB = keyB + base;
+  unsigned* vA = valA + base; unsigned* vB = valB + base;
+  for (int i = tid; i < n; i += NT2) {
+    const long long pp = piece_pos(pre, nch, i, base);
+    const float4 q = surf[pp];
+    const int cx = surf_cell(q.x, P.sx0, P.sg_inv, P.sg_nx), cy = surf_cell(q.y, P.sy0, P.sg_inv, P.sg_ny);
+    kA[i] = ((unsigned)cy << P.sg_bx) | (unsigned)cx;
+    vA[i] = (unsigned)(pp - base);
+  }
+  const int keybits = P.sg_bx + bits_for(P.sg_ny - 1);
+  unsigned *kS = kA, *kT = kB, *vS = vA, *vT = vB;
+  for (int shift = 0; shift < keybits; shift += 8) {
+    unsigned* ki = kS; unsigned* ko = kT; unsigned* vi = vS; unsigned* vo = vT;
+    block_radix_pass<NT2, unsigned>(
+        n, [=](int i) { return (ki[i] >> shift) & 255u; },
+        [=](int i, int pos) { ko[pos] = ki[i]; vo[pos] = vi[i]; }, wc, rbase);
+    kS = ko; kT = ki; vS = vo; vT = vi;
+  }
+  __syncthreads();
+  float4* so = sorted + base;
+  unsigned* sk = sortedKey + base;
+  for (int i = tid; i < n; i += NT2) {
+    const unsigned k = kS[i];
+    so[i] = surf[base + vS[i]];
+    sk[i] = k;
+    const int r = (int)(k >> P.sg_bx);
+    const int rp = (i == 0) ? -1 : (int)(kS[i - 1] >> P.sg_bx);
+    for (int rr = rp + 1; rr <= r; rr++) rs[rr] = i;
+    if (i == n - 1) for (int rr = r + 1; rr <= P.sg_ny; rr++) rs[rr] = n;
+  }
+}
+
+// span of sorted positions of row r whose cell x is in [cx0, cx1]
+__device__ __forceinline__ void row_span(const unsigned* __restrict__ sk, const int* __restrict__ rs,
+                                         int r, int cx0, int cx1, int bx, int& b, int& e) {
+  const int rb = rs[r], re = rs[r + 1];
+  const unsigned klo = ((unsigned)r << bx) | (unsigned)cx0, khi = ((unsigned)r << bx) | (unsigned)cx1;
+  int lo = rb, hi = re;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] < klo) lo = mid + 1; else hi = mid; }
+  b = lo;
+  hi = re;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] <= khi) lo = mid + 1; else hi = mid; }
+  e = lo;
+}
+
+// ============================================================================================
+// K4b — mark the surface points inside the search sphere of any keypoint (3dsc.hpp
+// searchForNeighbors with search_radius_), count each keypoint's neighbours.
+// rho[i] = -(scan+1) marks "density needed".  One block per keypoint, grid-stride.
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_desc_mark(
+    const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
+    int n_scans, const float4* __restrict__ sorted, const unsigned* __restrict__ sortedKey,
+    const int* __restrict__ rowStart, const long long* __restrict__ scan_off, DevParams P,
+    int* __restrict__ rho, int* __restrict__ kpNbr) {
+  __shared__ int s_cnt;
+  const int total = kpOff[n_scans];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const float4 o = kpOut[g];
+    const int s = kpScan[g];
+    int cnt = 0;
+    if (finite3(o.x, o.y, o.z)) {
+      const long long base = scan_off[s];
+      const float4* so = sorted + base;
+      const unsigned* sk = sortedKey + base;
+      const int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+      const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
+      const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
+      for (int r = cy0 + w; r <= cy1; r += 8) {
+        int b, e;
+        row_span(sk, rs, r, cx0, cx1, P.sg_bx, b, e);
+        for (int i = b + lane; i < e; i += 32) {
+          const float4 q = so[i];
+          const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
+          if (d2 < P.R2f) { cnt++; rho[base + i] = -(s + 1); }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FE_FULL, cnt, d);
+    if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) kpNbr[g] = s_cnt;
+    __syncthreads();
+  }
+}
+
+// ============================================================================================
+// K4c — local point density (3dsc.hpp: searchForNeighbors(point_density_radius_)), once per
+// marked surface point instead of once per (keypoint, neighbour) as PCL does.
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_density(
+    const float4* __restrict__ sorted, const unsigned* __restrict__ sortedKey,
+    const int* __restrict__ rowStart, const long long* __restrict__ scan_off, DevParams P,
+    long long total, int* __restrict__ rho) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = rho[i];
+    if (v >= 0) continue;
+    const int s = -v - 1;
+    const long long base = scan_off[s];
+    const float4* so = sorted + base;
+    const unsigned* sk = sortedKey + base;
+    const int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+    const float4 p = sorted[i];
+    const unsigned key = sortedKey[i];
+    const int cx = (int)(key & ((1u << P.sg_bx) - 1u)), cy = (int)(key >> P.sg_bx);
+    // cells reached by the density radius (>= 1 cell each way; more only if the grid was capped)
+    const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, P.sg_nx);
+    const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, P.sg_ny);
+    (void)cx; (void)cy;
+    int cnt = 0;
+    for (int r = cy0; r <= cy1; r++) {
+      int b, e;
+      row_span(sk, rs, r, cx0, cx1, P.sg_bx, b, e);
+      for (int j = b; j < e; j++) {
+        const float4 q = so[j];
+        // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
+        if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+      }
+    }
+    rho[i] = cnt;
+  }
+}
+
+// ============================================================================================
+// K4d — the 1980-bin 3D shape context of one keypoint per block (3dsc.hpp computePoint).
+// ============================================================================================
+__device__ __forceinline__ float eigen_sum3(float a0, float a1, float a2) {
+  return __fadd_rn(a0, __fadd_rn(a1, a2));  // Eigen's unrolled 3-term reduction: a0 + (a1 + a2)
+}
+
+__global__ void __launch_bounds__(256) k_desc_hist(
+    const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
+    int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted,
+    const unsigned* __restrict__ sortedKey, const int* __restrict__ rowStart,
+    const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
+    const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
+    float* __restrict__ desc, DevCounters* __restrict__ ctr) {
+  __shared__ float hist[FE_DESC_LEN];
+  __shared__ int s_rank;
+  const int total = kpOff[n_scans];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    float* out = desc + (long long)g * FE_DESC_LEN;
+    const int nb = kpNbr[g];
+    if (nb == 0) {  // no neighbour (or non-finite keypoint): descriptor is NaN (3dsc.hpp)
+      for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) out[i] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    const int s = kpScan[g];
+    for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) hist[i] = 0.0f;
+    if (threadIdx.x == 0) s_rank = 0;
+    __syncthreads();
+    // the RNG is consumed only by keypoints that have neighbours, in keypoint order
+    {
+      int c = 0;
+      for (int j = kpOff[s] + threadIdx.x; j < g; j += blockDim.x) c += (kpNbr[j] > 0) ? 1 : 0;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FE_FULL, c, d);
+      if (lane == 0 && c) atomicAdd(&s_rank, c);
+    }
+    __syncthreads();
+    const int rank = s_rank;
+    if (rank >= axesCap) {
+      if (threadIdx.x == 0) atomicOr(&ctr->err, ERR_AXIS_CAP);
+      for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) out[i] = __int_as_float(0x7fc00000);
+      __syncthreads();
+      continue;
+    }
+    const float2 ax = axes[rank];  // normalised x_axis = (ax.x, ax.y, -0)
+    const float axz = -0.0f;
+    const float4 o = kpOut[g];
+    const long long base = scan_off[s];
+    const float4* so = sorted + base;
+    const unsigned* sk = sortedKey + base;
+    const int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+    const int* rh = rho + base;
+    const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
+    const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
+    for (int r = cy0 + w; r <= cy1; r += 8) {
+      int b, e;
+      row_span(sk, rs, r, cx0, cx1, P.sg_bx, b, e);
+      for (int i = b + lane; i < e; i += 32) {
+        const float4 q = so[i];
+        const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
+        if (!(d2 < P.R2f)) continue;
+        if (fabsf(d2 - 0.0f) < 1.17549435e-38f) continue;  // pcl::utils::equal(nn_dists, 0)
+        const float rr = __fsqrt_rn(d2);
+        // pcl::geometry::project(neighbour, origin, normal=(0,0,1), proj); proj -= origin
+        const float pox = __fsub_rn(q.x, o.x), poy = __fsub_rn(q.y, o.y), poz = __fsub_rn(q.z, o.z);
+        const float lambda = eigen_sum3(__fmul_rn(0.0f, pox), __fmul_rn(0.0f, poy), __fmul_rn(1.0f, poz));
+        float prx = __fsub_rn(__fsub_rn(q.x, __fmul_rn(lambda, 0.0f)), o.x);
+        float pry = __fsub_rn(__fsub_rn(q.y, __fmul_rn(lambda, 0.0f)), o.y);
+        float prz = __fsub_rn(__fsub_rn(q.z, __fmul_rn(lambda, 1.0f)), o.z);
+        {  // Eigen 3.2 normalize(): multiply by 1/norm
+          const float inv = __fdiv_rn(1.0f, __fsqrt_rn(eigen_sum3(__fmul_rn(prx, prx), __fmul_rn(pry, pry), __fmul_rn(prz, prz))));
+          prx = __fmul_rn(prx, inv); pry = __fmul_rn(pry, inv); prz = __fmul_rn(prz, inv);
+        }
+        // cross = x_axis x proj
+        const float crx = __fsub_rn(__fmul_rn(ax.y, prz), __fmul_rn(axz, pry));
+        const float cry = __fsub_rn(__fmul_rn(axz, prx), __fmul_rn(ax.x, prz));
+        const float crz = __fsub_rn(__fmul_rn(ax.x, pry), __fmul_rn(ax.y, prx));
+        const float crn = __fsqrt_rn(eigen_sum3(__fmul_rn(crx, crx), __fmul_rn(cry, cry), __fmul_rn(crz, crz)));
+        const float dt = eigen_sum3(__fmul_rn(ax.x, prx), __fmul_rn(ax.y, pry), __fmul_rn(axz, prz));
+        // atan2f / acosf through double so that the float result is (almost always) correctly rounded
+        float phi = __fmul_rn((float)atan2((double)crn, (double)dt), 57.29578f);
+        const float cdn = eigen_sum3(__fmul_rn(crx, 0.0f), __fmul_rn(cry, 0.0f), __fmul_rn(crz, 1.0f));
+        phi = (cdn < 0.f) ? __fsub_rn(360.0f, phi) : phi;
+        float nox = pox, noy = poy, noz = poz;
+        {
+          const float inv = __fdiv_rn(1.0f, __fsqrt_rn(eigen_sum3(__fmul_rn(nox, nox), __fmul_rn(noy, noy), __fmul_rn(noz, noz))));
+          nox = __fmul_rn(nox, inv); noy = __fmul_rn(noy, inv); noz = __fmul_rn(noz, inv);
+        }
+        float th = eigen_sum3(__fmul_rn(0.0f, nox), __fmul_rn(0.0f, noy), __fmul_rn(1.0f, noz));
+        const float t1 = (-1.0f < th) ? th : -1.0f;  // std::max(-1.0f, theta)
+        const float t2 = (t1 < 1.0f) ? t1 : 1.0f;    // std::min(1.0f, .)
+        th = __fmul_rn((float)acos((double)t2), 57.29578f);
+        int j = 0, k = 0, l = 0;
+#pragma unroll
+        for (int a = 15; a >= 1; a--) if (rr <= P.radii[a]) j = a - 1;
+#pragma unroll
+        for (int a = 11; a >= 1; a--) if (th <= P.theta[a]) k = a - 1;
+#pragma unroll
+        for (int a = 12; a >= 1; a--) if (phi <= P.phi[a]) l = a - 1;
+        const int dens = rh[i];
+        if (dens <= 0) continue;
+        const int bin = l * 165 + k * 15 + j;
+        const float wgt = __fmul_rn(__fdiv_rn(1.0f, (float)dens), lut[bin]);
+        atomicAdd(&hist[bin], wgt);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) out[i] = hist[i];
+    __syncthreads();
+  }
+}
+
+}  // namespace fe
