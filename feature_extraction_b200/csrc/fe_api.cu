@@ -33,6 +33,7 @@ struct Slot {
   int *d_kfBase = nullptr, *d_kfCnt = nullptr, *d_kcBase = nullptr, *d_kcCnt = nullptr;
   int *d_kpBase = nullptr, *d_kpCnt = nullptr, *d_kpOff = nullptr, *d_kpScan = nullptr, *d_kpNbr = nullptr;
   int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
+  int *d_ovfRings = nullptr, *d_ovfMerge = nullptr;
   int64_t capRowStart = 0;
   float4 *d_kfPool = nullptr, *d_kcPool = nullptr, *d_kpPool = nullptr, *d_kpOut = nullptr, *d_gather = nullptr;
   float* d_desc = nullptr;
@@ -214,7 +215,7 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfMerge, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
   for (void* p : hv) if (p) cudaFreeHost(p);
@@ -252,6 +253,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_kpBase, ns)); CK(dalloc(&s.d_kpCnt, ns)); CK(dalloc(&s.d_kpOff, ns + 1));
   CK(dalloc(&s.d_kpScan, (size_t)s.capKp)); CK(dalloc(&s.d_kpNbr, (size_t)s.capKp));
   CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1));
+  CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfMerge, ns));
   CK(dalloc(&s.d_kfPool, (size_t)s.capKf)); CK(dalloc(&s.d_kpPool, (size_t)s.capKp)); CK(dalloc(&s.d_kpOut, (size_t)s.capKp));
   CK(dalloc(&s.d_desc, (size_t)s.capKp * FE_DESC_LEN));
   CK(dalloc(&s.d_ctr, 1));
@@ -330,13 +332,42 @@ int ensure_kc(fe_ctx* ctx, Slot& s) {
   return FE_OK;
 }
 
-const size_t kClusterSmem = cluster_smem_bytes();
+const size_t kClusterSmem = cluster_smem_bytes(ECAP);
+const size_t kClusterSmemL = cluster_smem_bytes(ECAP_L);
 
 int set_kernel_attrs(fe_ctx* ctx) {
-  CK(cudaFuncSetAttribute(k_cluster_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_merge_keypoints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   return FE_OK;
+}
+
+// K2 + K3 for `nscans` scans: the 2-blocks-per-SM instantiation first, then the large one over
+// whatever scans it deferred (an immediate exit when there are none).
+void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool wantKc, bool merge) {
+  const DevParams& P = ctx->dp;
+  const int gridL = std::min(nscans, 148);
+  int* ovfR = &s.d_ctr->ovf_rings;
+  int* ovfM = &s.d_ctr->ovf_merge;
+  float4* kc = wantKc ? s.d_kcPool : nullptr;
+  int* kcB = wantKc ? s.d_kcBase : nullptr;
+  int* kcC = wantKc ? s.d_kcCnt : nullptr;
+  k_cluster_rings<ECAP, 2><<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
+                                                                    singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
+                                                                    s.capKc, kcB, kcC, s.d_ctr, nullptr, nullptr, s.d_ovfRings);
+  k_cluster_rings<ECAP_L, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
+                                                                      singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
+                                                                      s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr);
+  ctx->launches += 2;
+  if (merge) {
+    k_merge_keypoints<ECAP, 2><<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
+                                                                        s.d_kpBase, s.d_kpCnt, s.d_ctr, nullptr, nullptr, s.d_ovfMerge);
+    k_merge_keypoints<ECAP_L, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
+                                                                          s.d_kpBase, s.d_kpCnt, s.d_ctr, s.d_ovfMerge, ovfM, nullptr);
+    ctx->launches += 2;
+  }
 }
 
 // Enqueue the kernels of one sub-batch whose points are at d_pts.  k1flags selects what K1 does;
@@ -353,21 +384,14 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     ctx->launches++;
   }
   mark(ctx, s, "K1 level+crop+ring");
-  k_cluster_rings<<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
-                                                           singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt,
-                                                           wantKc ? s.d_kcPool : nullptr, s.capKc, wantKc ? s.d_kcBase : nullptr,
-                                                           wantKc ? s.d_kcCnt : nullptr, s.d_ctr);
-  ctx->launches++;
-  mark(ctx, s, "K2 ring clusters");
-  k_merge_keypoints<<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
-                                                             s.d_kpBase, s.d_kpCnt, nullptr, nullptr, s.d_ctr);
-  ctx->launches++;
+  launch_clustering(ctx, s, nscans, singleRing, wantKc, true);
+  mark(ctx, s, "K2+K3 ring clusters + merge");
   k_kp_offsets<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr);
   ctx->launches++;
   k_kp_gather<<<std::max(1, std::min(1024, (nscans * 8 + 255) / 256)), 256, 0, s.stream>>>(s.d_kpPool, s.d_kpBase, s.d_kpOff, nscans,
                                                                                             s.d_kpOut, s.d_kpScan);
   ctx->launches++;
-  mark(ctx, s, "K3 merge keypoints");
+  mark(ctx, s, "keypoint CSR");
   if (doDesc) {
     int st = ensure_rowstart(ctx, s, nscans);
     if (st) return st;
@@ -722,6 +746,13 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int
   return FE_OK;
 }
 
+int fe_download(fe_ctx_t* ctx, void* host_dst, const void* device_src, int64_t bytes) {
+  if (!ctx || bytes < 0 || (bytes > 0 && (!host_dst || !device_src))) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (bytes > 0) CK(cudaMemcpy(host_dst, device_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return FE_OK;
+}
+
 // ---- one entry point per reference function ----------------------------------------------------------
 
 static int stage_k1(fe_ctx* ctx, fe_point_t* cloud, int64_t n, double roll, double pitch, int flags) {
@@ -816,7 +847,7 @@ int fe_extract_clusters(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, doubl
   *n_clusters = 0;
   cluster_offsets[0] = 0;
   if (n == 0) return FE_OK;
-  if (n > ECAP) return fail(ctx, FE_ERR_CAPACITY, "fe_extract_clusters: cloud larger than the per-block capacity");
+  if (n > ECAP_L) return fail(ctx, FE_ERR_CAPACITY, "fe_extract_clusters: cloud larger than the per-block capacity");
   if (!(tolerance > 0.0)) return fail(ctx, FE_ERR_INVALID, "tolerance must be > 0");
   Slot& s = ctx->slot[0];
   int st = ensure_slot(ctx, s, true);
@@ -827,7 +858,7 @@ int fe_extract_clusters(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, doubl
   int* d_off = (int*)s.d_keyA;
   int* d_idx = (int*)s.d_keyB;
   int* d_n = (int*)s.d_valA;
-  k_extract_clusters_stage<<<1, NT2, kClusterSmem, s.stream>>>(s.d_pts, (int)n, tol_f, r2f, min_size, max_size, d_off, (int)n, d_idx, d_n);
+  k_extract_clusters_stage<<<1, NT2, kClusterSmemL, s.stream>>>(s.d_pts, (int)n, tol_f, r2f, min_size, max_size, d_off, (int)n, d_idx, d_n);
   ctx->launches++;
   CK(cudaGetLastError());
   int nc = 0;
@@ -857,15 +888,7 @@ static int stage_keypoints(fe_ctx* ctx, const fe_point_t* cloud, int64_t n, bool
   st = stage_upload_k1(ctx, s, cloud, n, singleRing ? 0 : F_RING, &nch);
   if (st) return st;
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), s.stream));
-  k_cluster_rings<<<1, NT2, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, ctx->dp,
-                                                      singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, s.d_kcPool,
-                                                      s.capKc, s.d_kcBase, s.d_kcCnt, s.d_ctr);
-  ctx->launches++;
-  if (merge) {
-    k_merge_keypoints<<<1, NT2, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, ctx->dp, s.d_kpPool, (int)s.capKp,
-                                                          s.d_kpBase, s.d_kpCnt, nullptr, nullptr, s.d_ctr);
-    ctx->launches++;
-  }
+  launch_clustering(ctx, s, 1, singleRing, true, merge);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
@@ -978,6 +1001,13 @@ int fe_pack_point_descriptors(const fe_point_t* keypoints, const float* descript
     // rf[9] at r + 5 + 1980 stays zero (3dsc.hpp zeroes it); 2 floats of tail padding (EIGEN_ALIGN16)
   }
   return FE_OK;
+}
+
+// debug / test hook: keypoints_full (src:205), i.e. estimateKeypoints before the cross-ring merge
+int fe_debug_keypoints_full(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, fe_point_t* kf, int64_t cap, int64_t* n_kf) {
+  if (!ctx || n < 0 || (n > 0 && !cloud)) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return stage_keypoints(ctx, cloud, n, false, false, kf, cap, n_kf, nullptr, 0, nullptr);
 }
 
 // debug / test hook: the cluster order PCL's final std::sort leaves, from the replay the kernels use

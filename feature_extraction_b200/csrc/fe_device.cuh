@@ -147,6 +147,15 @@ __device__ __forceinline__ unsigned uf_find(unsigned* parent_, unsigned a) {
   return a;
 }
 
+// Read-only find for the flatten pass: with every thread storing its own final label, a
+// concurrent path-halving store could overwrite an already flattened entry with a stale ancestor.
+__device__ __forceinline__ unsigned uf_find_readonly(const unsigned* parent_, unsigned a) {
+  const volatile unsigned* parent = parent_;
+  unsigned p = parent[a];
+  while (p != a) { a = p; p = parent[a]; }
+  return a;
+}
+
 __device__ __forceinline__ void uf_union(unsigned* parent, unsigned a, unsigned b) {
   for (;;) {
     a = uf_find(parent, a);

@@ -24,7 +24,8 @@ namespace fe {
 constexpr int CH = 2048;        // points per K1 chunk (one block)
 constexpr int MAXCHUNK = 1024;  // chunks per scan the per-scan kernels can index (2M points)
 constexpr int NT2 = 512;        // threads of the per-scan clustering / grid kernels
-constexpr int ECAP = 2944;      // cluster entries a block holds in shared memory at once
+constexpr int ECAP = 2944;      // cluster entries a block holds in shared memory (2 blocks / SM)
+constexpr int ECAP_L = 6528;    // the large instantiation (1 block / SM) for scans the fast one defers
 
 // error bits reported through DevCounters::err
 enum {
@@ -67,7 +68,9 @@ struct DevCounters {
   int kc_cursor;   // keypoint_cloud pool
   int err;
   int kp_total;
-  int pad[3];
+  int ovf_rings;   // scans deferred from K2 to its large instantiation
+  int ovf_merge;   // scans deferred from K3 to its large instantiation
+  int pad[1];
 };
 
 // ============================================================================================
@@ -216,23 +219,24 @@ struct ClusterSm {
   int* misc;               // MISC_INTS
 };
 constexpr int MISC_INTS = MAXCHUNK + 1 + 128;
-constexpr size_t cluster_smem_bytes() {
-  return (size_t)ECAP * (12 + 4 + 1 + 8 + 8) + (NT2 / 32) * 257 * 2 + (256 + 32) * 4 + MISC_INTS * 4 + 64;
+constexpr size_t cluster_smem_bytes(int cap) {
+  return (size_t)cap * (12 + 4 + 1 + 8 + 8) + (NT2 / 32) * 257 * 2 + (256 + 32) * 4 + MISC_INTS * 4 + 64;
 }
 
+template <int CAP>
 __device__ __forceinline__ void cluster_sm_carve(unsigned char* p, ClusterSm& S) {
-  S.x = (float*)p; p += ECAP * 4;
-  S.y = (float*)p; p += ECAP * 4;
-  S.z = (float*)p; p += ECAP * 4;
-  S.gref = (unsigned*)p; p += ECAP * 4;
-  S.keyA = (unsigned*)p; p += ECAP * 4;
-  S.keyB = (unsigned*)p; p += ECAP * 4;
+  S.x = (float*)p; p += CAP * 4;
+  S.y = (float*)p; p += CAP * 4;
+  S.z = (float*)p; p += CAP * 4;
+  S.gref = (unsigned*)p; p += CAP * 4;
+  S.keyA = (unsigned*)p; p += CAP * 4;
+  S.keyB = (unsigned*)p; p += CAP * 4;
   S.base = (unsigned*)p; p += (256 + 32) * 4;
   S.misc = (int*)p; p += MISC_INTS * 4;
-  S.valA = (unsigned short*)p; p += ECAP * 2;
-  S.valB = (unsigned short*)p; p += ECAP * 2;
-  S.aux = (unsigned short*)p; p += ECAP * 2;
-  S.lst = (unsigned short*)p; p += ECAP * 2;
+  S.valA = (unsigned short*)p; p += CAP * 2;
+  S.valB = (unsigned short*)p; p += CAP * 2;
+  S.aux = (unsigned short*)p; p += CAP * 2;
+  S.lst = (unsigned short*)p; p += CAP * 2;
   S.wc = (unsigned short*)p; p += (NT2 / 32) * 257 * 2;
   S.ring = (unsigned char*)p;
 }
@@ -353,7 +357,7 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
   __syncthreads();
   // ---- flatten, component sizes ----
   unsigned* cnt = kS;
-  for (int e = tid; e < E; e += NT) { parent[e] = uf_find(parent, (unsigned)e); cnt[e] = 0; }
+  for (int e = tid; e < E; e += NT) { parent[e] = uf_find_readonly(parent, (unsigned)e); cnt[e] = 0; }
   __syncthreads();
   for (int e = tid; e < E; e += NT) atomicAdd(&cnt[parent[e]], 1u);
   __syncthreads();
@@ -475,17 +479,15 @@ __device__ __forceinline__ long long piece_pos(const int* pre, int nch, int i, l
 // ============================================================================================
 // K2 — per-ring clustering and getCylinderSegments gating for one scan per block.
 // ============================================================================================
-__global__ void __launch_bounds__(NT2, 2) k_cluster_rings(
-    const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta,
+template <int CAP>
+__device__ void cluster_rings_scan(
+    ClusterSm& S, const int s, const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta,
     const int* __restrict__ cropCnt, const long long* __restrict__ scan_off,
-    const int* __restrict__ chunk_off, DevParams P, int single_ring,
+    const int* __restrict__ chunk_off, const DevParams& P, int single_ring,
     float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
     float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
-    DevCounters* __restrict__ ctr) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ClusterSm S;
-  cluster_sm_carve(smem_raw, S);
-  const int s = blockIdx.x, tid = threadIdx.x;
+    DevCounters* __restrict__ ctr, int* __restrict__ ovfList) {
+  const int tid = threadIdx.x;
   int* pre = S.misc;
   int* sc = S.misc + MAXCHUNK + 1;
   int* ringCnt = sc + 80;  // 16
@@ -507,16 +509,23 @@ __global__ void __launch_bounds__(NT2, 2) k_cluster_rings(
   }
   __syncthreads();
   const int nRingsAll = single_ring ? 1 : 16;
+  {
+    int big = 0;
+    for (int r = 0; r < nRingsAll; r++) big = max(big, ringCnt[r]);
+    if (big > CAP) {  // a single ring is larger than this instantiation's capacity
+      if (tid == 0) {
+        if (ovfList) ovfList[atomicAdd(&ctr->ovf_rings, 1)] = s;  // the large instantiation takes it
+        else atomicOr(&ctr->err, ERR_RING_CAP);
+      }
+      return;
+    }
+  }
   int group = 0;
   int r0 = 0;
   while (r0 < nRingsAll) {
     // greedy run of consecutive rings that fits the shared-memory capacity
     int r1 = r0, tot = 0;
-    while (r1 < nRingsAll && tot + ringCnt[r1] <= ECAP) { tot += ringCnt[r1]; r1++; }
-    if (r1 == r0) {  // a single ring is larger than the capacity
-      if (tid == 0) atomicOr(&ctr->err, ERR_RING_CAP);
-      return;
-    }
+    while (r1 < nRingsAll && tot + ringCnt[r1] <= CAP) { tot += ringCnt[r1]; r1++; }
     if (tot > 0) {
       // ---- gather the entries of rings [r0, r1) in original order ----
       int run = 0;
@@ -633,19 +642,44 @@ __global__ void __launch_bounds__(NT2, 2) k_cluster_rings(
   }
 }
 
+// scanList == nullptr: block b handles scan b and defers oversized scans to ovfList;
+// otherwise the blocks loop over scanList[0 .. *nList) (the deferred scans).
+template <int CAP, int MINB>
+__global__ void __launch_bounds__(NT2, MINB) k_cluster_rings(
+    const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta,
+    const int* __restrict__ cropCnt, const long long* __restrict__ scan_off,
+    const int* __restrict__ chunk_off, DevParams P, int single_ring,
+    float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
+    float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
+    DevCounters* __restrict__ ctr, const int* __restrict__ scanList, const int* __restrict__ nList,
+    int* __restrict__ ovfList) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClusterSm S;
+  cluster_sm_carve<CAP>(smem_raw, S);
+  if (!scanList) {
+    cluster_rings_scan<CAP>(S, blockIdx.x, crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
+                            kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfList);
+  } else {
+    const int n = *nList;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+      __syncthreads();
+      cluster_rings_scan<CAP>(S, scanList[i], crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
+                              kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, nullptr);
+    }
+  }
+}
+
 // ============================================================================================
 // K3 — cross-ring merge (src:205-257) for one scan per block; also the stage kernel behind
 // fe_extract_clusters when `stage` != 0 (then it just reports the clusters of `crop`).
 // ============================================================================================
-__global__ void __launch_bounds__(NT2, 2) k_merge_keypoints(
-    const float4* __restrict__ kfPool, const int* __restrict__ kfBase, const int* __restrict__ kfCnt,
-    DevParams P, float4* __restrict__ kpPool, int kpCap, int* __restrict__ kpBase,
-    int* __restrict__ kpCnt, float4* __restrict__ kfOut, int* __restrict__ kfOutCnt,
-    DevCounters* __restrict__ ctr) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ClusterSm S;
-  cluster_sm_carve(smem_raw, S);
-  const int s = blockIdx.x, tid = threadIdx.x;
+template <int CAP>
+__device__ void merge_keypoints_scan(
+    ClusterSm& S, const int s, const float4* __restrict__ kfPool, const int* __restrict__ kfBase,
+    const int* __restrict__ kfCnt, const DevParams& P, float4* __restrict__ kpPool, int kpCap,
+    int* __restrict__ kpBase, int* __restrict__ kpCnt, DevCounters* __restrict__ ctr,
+    int* __restrict__ ovfList) {
+  const int tid = threadIdx.x;
   int* sc = S.misc + MAXCHUNK + 1;
   int* pre = S.misc;  // 17 prefix entries of the pieces
   if (tid == 0) {
@@ -656,9 +690,14 @@ __global__ void __launch_bounds__(NT2, 2) k_merge_keypoints(
   }
   __syncthreads();
   const int Kf = pre[16];
-  if (kfOutCnt && tid == 0) kfOutCnt[s] = Kf;
   if (Kf == 0) return;
-  if (Kf > ECAP) { if (tid == 0) atomicOr(&ctr->err, ERR_MERGE_CAP); return; }
+  if (Kf > CAP) {
+    if (tid == 0) {
+      if (ovfList) ovfList[atomicAdd(&ctr->ovf_merge, 1)] = s;  // the large instantiation takes it
+      else atomicOr(&ctr->err, ERR_MERGE_CAP);
+    }
+    return;
+  }
   for (int i = tid; i < Kf; i += NT2) {
     int g = 0;
     while (g < 15 && pre[g + 1] <= i) g++;
@@ -669,7 +708,6 @@ __global__ void __launch_bounds__(NT2, 2) k_merge_keypoints(
     S.z[i] = (float)__ddiv_rn(__dmul_rn(__dmul_rn((double)q.w, 0.75), P.radius_threshold), 2.0);
     S.gref[i] = (unsigned)src;
     S.ring[i] = 0;
-    if (kfOut) kfOut[(long long)s * ECAP + i] = q;
   }
   __syncthreads();
   ClusterOut C;
@@ -706,13 +744,33 @@ __global__ void __launch_bounds__(NT2, 2) k_merge_keypoints(
   }
 }
 
+template <int CAP, int MINB>
+__global__ void __launch_bounds__(NT2, MINB) k_merge_keypoints(
+    const float4* __restrict__ kfPool, const int* __restrict__ kfBase, const int* __restrict__ kfCnt,
+    DevParams P, float4* __restrict__ kpPool, int kpCap, int* __restrict__ kpBase,
+    int* __restrict__ kpCnt, DevCounters* __restrict__ ctr, const int* __restrict__ scanList,
+    const int* __restrict__ nList, int* __restrict__ ovfList) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClusterSm S;
+  cluster_sm_carve<CAP>(smem_raw, S);
+  if (!scanList) {
+    merge_keypoints_scan<CAP>(S, blockIdx.x, kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, ovfList);
+  } else {
+    const int n = *nList;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+      __syncthreads();
+      merge_keypoints_scan<CAP>(S, scanList[i], kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, nullptr);
+    }
+  }
+}
+
 // Stage kernel: plain EuclideanClusterExtraction of n points (one block), CSR result.
-__global__ void __launch_bounds__(NT2, 2) k_extract_clusters_stage(
+__global__ void __launch_bounds__(NT2, 1) k_extract_clusters_stage(
     const float4* __restrict__ pts, int n, float tol_f, float r2f, int minSz, int maxSz,
     int* __restrict__ offsets, int capClusters, int* __restrict__ indices, int* __restrict__ nOut) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
-  cluster_sm_carve(smem_raw, S);
+  cluster_sm_carve<ECAP_L>(smem_raw, S);
   const int tid = threadIdx.x;
   for (int i = tid; i < n; i += NT2) {
     const float4 q = pts[i];

@@ -16,6 +16,9 @@
 #else
 #define FE_HD inline
 #endif
+#if defined(__CUDACC__)
+#pragma nv_diag_suppress 20013, 20015  // host lambdas are only ever called from the host instantiation
+#endif
 
 namespace fe {
 

@@ -165,6 +165,16 @@ class FeatureExtractionNode:
                                                   _ptr(kc), cap, C.byref(n2)))
         return kp[: n1.value].copy(), kc[: n2.value].copy()
 
+    def debugKeypointsFull(self, cloud):
+        """keypoints_full of src:205 (test hook)."""
+        c = _cloud(cloud)
+        cap = max(2 * len(c), 1)
+        kf = np.empty((cap, 4), np.float32)
+        n1 = C.c_int64(0)
+        N.lib().fe_debug_keypoints_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        self._check(N.lib().fe_debug_keypoints_full(self._ctx, _ptr(c), len(c), _ptr(kf), cap, C.byref(n1)))
+        return kf[: n1.value].copy()
+
     def estimateDescriptors(self, cloud, keypoints):
         """src:329-355.  -> (K,1980) float32."""
         c = _cloud(cloud)
@@ -199,9 +209,9 @@ class FeatureExtractionNode:
         d = None
         if K > 0:
             kp = np.ctypeslib.as_array(C.cast(res.keypoints, C.POINTER(C.c_float)), shape=(K, 4))
-        if res.descriptors:
+        if self.params.estimate_descriptors:
             d = np.zeros((0, DESC_LEN), np.float32)
-            if K > 0:
+            if K > 0 and res.descriptors:
                 d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, DESC_LEN))
         if copy:
             return ko.copy(), kp.copy(), (d.copy() if d is not None else None)
@@ -220,6 +230,13 @@ class FeatureExtractionNode:
         self.last_launches = int(res.gpu_launches)
         ko = np.ctypeslib.as_array(res.keypoint_offsets, shape=(B + 1,)).copy()
         return ko, int(res.n_keypoints), res.keypoints, res.descriptors
+
+    def download(self, device_ptr, shape, dtype=np.float32):
+        """Copy a device-resident result of processBatchDevice to a new host array."""
+        out = np.empty(shape, dtype)
+        if out.nbytes:
+            self._check(N.lib().fe_download(self._ctx, _ptr(out), C.c_void_p(device_ptr), out.nbytes))
+        return out
 
     def enableCloudOutputs(self, enable=True):
         self._check(N.lib().fe_enable_cloud_outputs(self._ctx, 1 if enable else 0))

@@ -114,6 +114,9 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points,
                             const int64_t* scan_offsets, const double* roll_pitch,
                             int32_t n_scans, fe_batch_result_t* out);
 
+/* Copy `bytes` of a device-resident result (fe_process_batch_device) to host memory. */
+int fe_download(fe_ctx_t* ctx, void* host_dst, const void* device_src, int64_t bytes);
+
 /* Optional extra outputs of the last fe_process_batch() of ONE sub-batch (n_scans <=
  * max_scans_per_call): ~keypoint_cloud (src:133-135) and ~cloud (src:137-139), CSR by scan.
  * Enabled with fe_enable_cloud_outputs(ctx, 1) before the call. */

@@ -1,0 +1,151 @@
+"""Edge cases the reference handles by early return (src:209-210, 234-235, 263-264, 278-279,
+331-332) and size-independent properties at BASELINE.json's full batch size (needs a B200)."""
+import numpy as np
+import pytest
+
+from util import bits_equal, check_descriptors, to_fe_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def node(ob):
+    from feature_extraction_b200 import FeatureExtractionNode
+    n = FeatureExtractionNode(to_fe_params(ob.node_default()), max_points=8 << 20, max_scans=512, max_keypoints=1 << 15)
+    yield n
+    n.close()
+
+
+def test_empty_batch_and_empty_scans(ob, synth, node):
+    e = np.zeros((0, 4), np.float32)
+    ko, kp, d = node.processBatch(e, np.zeros(1, np.int64), np.zeros((0, 2)))
+    assert list(ko) == [0] and len(kp) == 0
+    ko, kp, d = node.processBatch(e, np.zeros(4, np.int64), np.zeros((3, 2)))
+    assert list(ko) == [0, 0, 0, 0] and len(kp) == 0 and d.shape == (0, 1980)
+    # ragged: empty scans between real ones
+    pts, offs, rp = synth.generate(2, 3)
+    offs2 = np.array([0, 0, offs[1], offs[1], offs[2], offs[3], offs[3]], np.int64)
+    rp2 = np.array([[0, 0], rp[0], [0, 0], rp[1], rp[2], [0, 0]])
+    ko, kp, d = node.processBatch(pts, offs2, rp2)
+    ko_o, kp_o, d_o, m = ob.process_batch(ob.node_default(), pts, offs2, rp2, mode=0, want_margin=True)
+    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o)
+    assert check_descriptors(d, d_o, m)[2] == 0
+    for fn in (node.getElevationAngles, node.rotateCloud, node.filterCloud):
+        assert len(fn(e)) == 0
+    assert node.extractClusters(e, 0.65, 1, 10) == []
+    assert all(len(x) == 0 for x in node.getCylinderSegments(e))
+    assert all(len(x) == 0 for x in node.estimateKeypoints(e))
+    assert node.estimateDescriptors(e, e).shape == (0, 1980)
+
+
+def test_non_finite_points_and_out_of_crop(ob, synth, node):
+    pts, offs, rp = synth.generate(2, 1, scan_index_base=7)
+    pts = pts.copy()
+    pts[5] = [np.nan, 1, 1, 0]
+    pts[100] = [np.inf, 0, 0, 0]
+    pts[200] = [1, -np.inf, 0, 0]
+    pts[300] = [0, 0, 0, 0]           # atan2(0,0)
+    pts[400] = [1e6, 1e6, 1e6, 0]
+    P = ob.node_default()
+    r = ob.process_scan(P, pts, rp[0, 0], rp[0, 1], mode=0)
+    ko, kp, d = node.processBatch(pts, offs, rp)
+    assert bits_equal(kp, r["keypoints"])
+    assert check_descriptors(d, r["descriptors"], r["edge_margin"])[2] == 0
+    el_g = node.getElevationAngles(pts)
+    el_o = ob.get_elevation_angles(pts)
+    fin = np.isfinite(el_o[:, 3])
+    assert bits_equal(el_g[fin], el_o[fin]) and np.array_equal(np.isnan(el_g[:, 3]), np.isnan(el_o[:, 3]))
+    assert bits_equal(node.filterCloud(r["cloud_full"]), r["cloud"])
+    # nothing inside the crop box -> no keypoints, not an error
+    far = pts.copy()
+    far[:, 0] -= 500.0
+    ko, kp, d = node.processBatch(far, offs, np.zeros((1, 2)))
+    assert ko[-1] == 0
+
+
+def test_point_on_a_ring_boundary_belongs_to_both_rings(ob, node):
+    # elevation exactly -14.0 lies in ring 0 ([-16,-14]) and ring 1 ([-14,-12]) (src:200-202)
+    P = ob.node_default()
+    c = []
+    for k in range(6):
+        c.append((10.0 + 0.02 * k, 1.0, -2.0, -15.0))
+    for k in range(6):
+        c.append((10.0 + 0.02 * k, 1.0, -1.6, -13.0))
+    c.append((10.05, 1.0, -1.8, -14.0))
+    c = np.array(c, np.float32)
+    kp_o, kc_o, kf_o = ob.estimate_keypoints(P, c)
+    kp_g, kc_g = node.estimateKeypoints(c)
+    assert len(kf_o) == 2 and len(kc_o) == 14  # the boundary point is dumped twice
+    assert bits_equal(kp_g, kp_o) and bits_equal(kc_g, kc_o)
+
+
+def test_zero_neighbour_keypoint_gives_nan_descriptor(ob, node):
+    P = ob.node_default()
+    cloud = np.array([[10, 0, 0, 0], [10.2, 0, 0.1, 0], [10.1, 0.3, 0.0, 0]], np.float32)
+    kps = np.array([[50, 0, 0, 0], [10.1, 0, 0, 0], [np.nan, 0, 0, 0], [10.0, 0.1, 0.05, 0]], np.float32)
+    d_o, m, nn = ob.estimate_descriptors(P, cloud, kps)
+    d_g = node.estimateDescriptors(cloud, kps)
+    assert np.all(np.isnan(d_g[0])) and np.all(np.isnan(d_g[2]))
+    assert check_descriptors(d_g, d_o, m)[2] == 0
+    # neighbour straight above the keypoint: NaN azimuth lands in bin l=0 on both sides
+    cloud2 = np.array([[10, 0, 1.0, 0], [10.3, 0.1, 0.0, 0]], np.float32)
+    kp2 = np.array([[10, 0, 0, 0]], np.float32)
+    d_o, m, nn = ob.estimate_descriptors(P, cloud2, kp2)
+    assert bits_equal(node.estimateDescriptors(cloud2, kp2), d_o)
+
+
+def test_capacity_overflow_is_an_error_not_truncation(ob, synth):
+    from feature_extraction_b200 import FeatureExtractionNode, FeatureExtractionError, _native
+    pts, offs, rp = synth.generate(2, 4)
+    small = FeatureExtractionNode(to_fe_params(ob.node_default()), max_points=20000, max_scans=4, max_keypoints=1)
+    with pytest.raises(FeatureExtractionError) as e:
+        small.processBatch(pts, offs, rp)
+    assert e.value.status == _native.FE_ERR_CAPACITY
+    small.close()
+    tiny = FeatureExtractionNode(to_fe_params(ob.node_default()), max_points=4096, max_scans=4, max_keypoints=64)
+    with pytest.raises(FeatureExtractionError) as e:
+        tiny.processBatch(pts, offs, rp)
+    assert e.value.status == _native.FE_ERR_CAPACITY
+    tiny.close()
+
+
+def test_idempotence_and_identity_properties(ob, synth, node):
+    pts, offs, rp = synth.generate(2, 1, scan_index_base=3)
+    node.roll, node.pitch = 0.0, 0.0
+    el = node.getElevationAngles(pts)
+    assert bits_equal(node.rotateCloud(el)[:, :3] + 0.0, el[:, :3] + 0.0)  # identity rotation (up to -0)
+    f1 = node.filterCloud(el)
+    assert bits_equal(node.filterCloud(f1), f1)                             # crop is idempotent
+    assert bits_equal(node.getElevationAngles(el), el)                      # el depends on xyz only
+
+
+def test_full_batch_size_properties(ob, synth):
+    """BASELINE.json config 2 at full size (10k scans): sub-batching must not change any result,
+    results are ordered by scan, and a random sample agrees with the oracle."""
+    from feature_extraction_b200 import FeatureExtractionNode
+    B = 10000
+    pts, offs, rp = synth.generate(2, B, scan_index_base=10_000)
+    P = ob.node_default()
+    a = FeatureExtractionNode(to_fe_params(P), max_points=48 << 20, max_scans=3000, max_keypoints=1 << 17)
+    ko_a, kp_a, d_a = a.processBatch(pts, offs, rp)
+    a.close()
+    b = FeatureExtractionNode(to_fe_params(P), max_points=6 << 20, max_scans=257, max_keypoints=1 << 15)
+    ko_b, kp_b, d_b = b.processBatch(pts, offs, rp)
+    assert np.array_equal(ko_a, ko_b) and bits_equal(kp_a, kp_b)
+    from util import rel_err
+    assert rel_err(d_a, d_b).max() < 1e-5           # only the float atomics' summation order differs
+    assert np.all(np.diff(ko_a) >= 0) and ko_a[-1] == len(kp_a) > B // 2
+    rng = np.random.default_rng(0)
+    sample = np.sort(rng.choice(B, 48, replace=False))
+    for s in sample:
+        r = ob.process_scan(P, pts[offs[s]:offs[s + 1]], rp[s, 0], rp[s, 1], mode=1)
+        assert bits_equal(kp_a[ko_a[s]:ko_a[s + 1]], r["keypoints"]), s
+        assert check_descriptors(d_a[ko_a[s]:ko_a[s + 1]], r["descriptors"], r["edge_margin"])[2] == 0
+    # a scan's result does not depend on its neighbours in the batch: reversed batch order
+    sel = sample[::-1]
+    p2 = np.concatenate([pts[offs[s]:offs[s + 1]] for s in sel])
+    o2 = np.concatenate([[0], np.cumsum([offs[s + 1] - offs[s] for s in sel])]).astype(np.int64)
+    ko_c, kp_c, d_c = b.processBatch(p2, o2, rp[sel])
+    for i, s in enumerate(sel):
+        assert bits_equal(kp_c[ko_c[i]:ko_c[i + 1]], kp_a[ko_a[s]:ko_a[s + 1]])
+    b.close()

@@ -1,0 +1,134 @@
+"""Parity of the CUDA path against the CPU oracle, through the C-ABI (needs a B200).
+
+Bar (BASELINE.json north_star): cluster membership and keypoint sets bit-exact; keypoint
+coordinates and descriptor values within 1e-5 relative (they are bit-exact in practice, descriptor
+bins differ only by float summation order); tolerance-boundary cases reported separately.
+"""
+import numpy as np
+import pytest
+
+from util import bits_equal, check_descriptors, rel_err, to_fe_params, DESC_RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(ob, cfg):
+    P = ob.launch_playback() if cfg == 1 else ob.node_default()
+    if cfg == 4:
+        P.descriptor_radius = 5.0
+    return P
+
+
+@pytest.fixture(scope="module")
+def nodes(ob):
+    from feature_extraction_b200 import FeatureExtractionNode
+    made = {}
+
+    def get(cfg):
+        if cfg not in made:
+            made[cfg] = FeatureExtractionNode(to_fe_params(_params(ob, cfg)), max_points=8 << 20, max_scans=512,
+                                              max_keypoints=1 << 15)
+        return made[cfg]
+    yield get
+    for n in made.values():
+        n.close()
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_each_reference_function_matches_the_oracle(ob, synth, nodes, cfg):
+    """Rows A-N of SURVEY.md §8(a), one C-ABI entry point per reference member function."""
+    P = _params(ob, cfg)
+    nd = nodes(cfg)
+    pts, offs, rp = synth.generate(cfg, 2)
+    for s in range(2):
+        sc = pts[offs[s]:offs[s + 1]]
+        r = ob.process_scan(P, sc, rp[s, 0], rp[s, 1], mode=0)
+        # A getElevationAngles (src:147-156)
+        el_o = ob.get_elevation_angles(sc)
+        assert bits_equal(nd.getElevationAngles(sc), el_o)
+        # B rotateCloud (src:159-167)
+        nd.roll, nd.pitch = rp[s]
+        assert bits_equal(nd.rotateCloud(el_o), ob.rotate_cloud(el_o, rp[s, 0], rp[s, 1]))
+        assert bits_equal(nd.rotateCloud(el_o), r["cloud_full"])
+        # D filterCloud (src:169-183)
+        assert bits_equal(nd.filterCloud(r["cloud_full"]), r["cloud"])
+        # E2 EuclideanClusterExtraction per ring (src:269-276): membership, member order, cluster order
+        for ring in (3, 6, 9):
+            rc = ob.select_ring(r["cloud"], ring)
+            if len(rc) == 0 or len(rc) > 2900:
+                continue
+            co = ob.extract_clusters(rc, P.cluster_tolerance, P.cluster_min_count, P.cluster_max_count)
+            cg = nd.extractClusters(rc, P.cluster_tolerance, P.cluster_min_count, P.cluster_max_count)
+            assert len(co) == len(cg)
+            assert all(np.array_equal(a, b) for a, b in zip(co, cg))
+            # F getCylinderSegments (src:261-327)
+            cen_o, cc_o = ob.get_cylinder_segments(P, rc)
+            cen_g, cc_g = nd.getCylinderSegments(rc)
+            assert bits_equal(cen_g, cen_o) and bits_equal(cc_g, cc_o)
+        # E1+G estimateKeypoints (src:185-259)
+        kp_o, kc_o, _ = ob.estimate_keypoints(P, r["cloud"])
+        kp_g, kc_g = nd.estimateKeypoints(r["cloud"])
+        assert bits_equal(kp_g, kp_o) and bits_equal(kc_g, kc_o)
+        assert bits_equal(kp_o, r["keypoints"])
+        # H-N estimateDescriptors (src:329-355)
+        if len(kp_o):
+            d_g = nd.estimateDescriptors(r["cloud_full"], kp_o)
+            ok, boundary, bad = check_descriptors(d_g, r["descriptors"], r["edge_margin"])
+            assert bad == 0, (ok, boundary, bad)
+
+
+@pytest.mark.parametrize("cfg,nscans", [(1, 6), (2, 48), (3, 3), (4, 4)])
+def test_fused_batch_matches_the_oracle(ob, synth, nodes, cfg, nscans):
+    """cloudCallback (src:83-117) in batch form, plus the ~cloud / ~keypoint_cloud outputs."""
+    P = _params(ob, cfg)
+    nd = nodes(cfg)
+    pts, offs, rp = synth.generate(cfg, nscans, scan_index_base=100)
+    nd.enableCloudOutputs(True)
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    co, cloud, kco, kcloud = nd.cloudOutputs(nscans)
+    nd.enableCloudOutputs(False)
+    ko_o, kp_o, d_o, m_o = ob.process_batch(P, pts, offs, rp, mode=0, n_threads=8, want_margin=True)
+    assert np.array_equal(ko, ko_o)
+    assert bits_equal(kp, kp_o)
+    ok, boundary, bad = check_descriptors(d, d_o, m_o)
+    assert bad == 0, (ok, boundary, bad)
+    assert boundary <= max(1, len(kp) // 50)
+    for s in range(nscans):
+        r = ob.process_scan(P, pts[offs[s]:offs[s + 1]], rp[s, 0], rp[s, 1], mode=1)
+        assert bits_equal(cloud[co[s]:co[s + 1]], r["cloud"])
+        assert bits_equal(kcloud[kco[s]:kco[s + 1]], r["keypoint_cloud"])
+
+
+def test_many_equal_size_clusters_follow_libstdcxx_sort_order(ob, nodes):
+    """> 16 clusters with ties: PCL's final std::sort is not stable; the device replays it."""
+    nd = nodes(2)
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        ncl = int(rng.integers(20, 150))
+        pts = []
+        for c in range(ncl):
+            size = int(rng.integers(1, 5))
+            cx, cy = 2.0 * (c % 40), 2.0 * (c // 40)
+            for k in range(size):
+                pts.append((cx + 0.05 * k, cy + 0.01 * rng.normal(), 0.0, -1.0))
+        pts = np.array(pts, np.float32)
+        pts = pts[rng.permutation(len(pts))]
+        co = ob.extract_clusters(pts, 0.65, 1, 1000)
+        cg = nd.extractClusters(pts, 0.65, 1, 1000)
+        assert len(co) == len(cg) == ncl
+        assert all(np.array_equal(a, b) for a, b in zip(co, cg))
+
+
+def test_device_resident_entry_point_equals_host_entry_point(ob, synth, nodes):
+    import torch
+    nd = nodes(2)
+    pts, offs, rp = synth.generate(2, 16, scan_index_base=500)
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    dev = torch.from_numpy(pts).cuda()
+    torch.cuda.synchronize()
+    ko2, K, p_kp, p_d = nd.processBatchDevice(dev.data_ptr(), offs, rp)
+    assert np.array_equal(ko, ko2) and K == len(kp)
+    assert bits_equal(nd.download(p_kp, (K, 4)), kp)
+    d2 = nd.download(p_d, (K, 1980))
+    from util import rel_err
+    assert rel_err(d2, d).max() < 1e-5

@@ -1,0 +1,108 @@
+"""Host-side logic of the product library that needs no GPU: the C-ABI loads and exports every
+symbol include/fe_b200.h declares, host helpers agree with the oracle, and the library fails
+loudly (no CPU fallback) when no device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from feature_extraction_b200 import _native
+    lib = _native.lib()
+    header = open(os.path.join(ROOT, "include", "fe_b200.h")).read()
+    declared = set(re.findall(r"\b(fe_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert b"sm_100a" in lib.fe_version()
+
+
+def test_struct_layouts_match_the_header():
+    from feature_extraction_b200 import _native
+    assert C.sizeof(_native.Params) == 6 * 8 + 8 + 4 + 4 + 8 + 4 + 4 + 8
+    assert C.sizeof(_native.Limits) == 32
+    assert C.sizeof(_native.BatchResult) == 56
+
+
+def test_presets_match_the_reference_defaults(ob):
+    from feature_extraction_b200 import node_default, launch_playback
+    for mine, theirs in ((node_default(), ob.node_default()), (launch_playback(), ob.launch_playback())):
+        for f, _ in mine._fields_:
+            assert getattr(mine, f) == getattr(theirs, f), f
+
+
+def test_rotation_matrix_host_helper_matches_oracle(ob):
+    from feature_extraction_b200 import rotation_matrix
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        r, p = rng.uniform(-3.5, 3.5, 2)
+        assert np.array_equal(rotation_matrix(r, p).view(np.uint32), ob.rotation_matrix(r, p).view(np.uint32))
+    assert np.array_equal(rotation_matrix(0.0, 0.0), np.eye(3, dtype=np.float32))
+
+
+def test_sort_replay_matches_libstdcxx_std_sort(ob):
+    from feature_extraction_b200.node import debug_sort_replay
+    rng = np.random.default_rng(5)
+    for t in range(1500):
+        n = int(rng.integers(1, 400))
+        hi = int(rng.integers(2, 60))
+        sizes = rng.integers(1, hi, n).astype(np.int32)
+        assert np.array_equal(debug_sort_replay(sizes), ob.std_sort_cluster_order(sizes))
+    # structured inputs: sorted, reversed, organ pipe, constant, few distinct values, large n
+    for n in (17, 33, 100, 1000, 5000):
+        base = np.arange(n, dtype=np.int32)
+        for sizes in (base, base[::-1].copy(), np.minimum(base, n - base), np.ones(n, np.int32), base % 3, base % 2):
+            sizes = np.ascontiguousarray(sizes, np.int32)
+            assert np.array_equal(debug_sort_replay(sizes), ob.std_sort_cluster_order(sizes))
+
+
+def test_sort_replay_heapsort_fallback_path(ob):
+    """Drive std::sort past its depth limit (median-of-3 killer) so the heap-sort branch runs."""
+    from feature_extraction_b200.node import debug_sort_replay
+    for n in (64, 256, 1024, 4096):
+        # Musser's median-of-3 killer sequence (on the reversed view the sort sees)
+        k = n // 2
+        a = np.zeros(n, np.int32)
+        for i in range(1, k + 1):
+            if i % 2 == 1:
+                a[i - 1] = i
+                a[i] = k + i
+            a[k + i - 1] = 2 * i
+        sizes = a[::-1].copy()
+        assert np.array_equal(debug_sort_replay(sizes), ob.std_sort_cluster_order(sizes))
+
+
+def test_pack_point_descriptors_layout():
+    from feature_extraction_b200 import pack_point_descriptors
+    kp = np.array([[1, 2, 3, 4], [5, 6, 7, 8]], np.float32)
+    d = np.arange(2 * 1980, dtype=np.float32).reshape(2, 1980)
+    rec = pack_point_descriptors(kp, d)
+    assert rec.shape == (2, 1996) and rec.nbytes == 2 * 7984
+    assert list(rec[1, :5]) == [5, 6, 7, 0, 8]
+    assert np.array_equal(rec[1, 5:1985], d[1])
+    assert np.all(rec[:, 1985:] == 0)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from feature_extraction_b200 import FeatureExtractionNode, FeatureExtractionError, _native
+    with pytest.raises(FeatureExtractionError) as e:
+        FeatureExtractionNode()
+    assert e.value.status == _native.FE_ERR_NO_DEVICE
+    assert _native.lib().fe_device_count() == 0
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "feature_extraction_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle_binding" not in txt and "libfe_oracle" not in txt and "fe_oracle" not in txt, (dp, f)
