@@ -45,7 +45,8 @@ struct Slot {
   DevCounters* h_ctr = nullptr;
   int* h_kpOff = nullptr;
   int* h_perScan = nullptr;
-  cudaEvent_t evDone = nullptr;
+  cudaEvent_t evDone = nullptr, evT0 = nullptr, evT1 = nullptr;
+  int lastNch = 0;
   // bookkeeping of the sub-batch in flight
   int nscans = 0;
   int64_t npts = 0;
@@ -221,6 +222,8 @@ void free_slot(Slot& s) {
   for (void* p : hv) if (p) cudaFreeHost(p);
   for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
   if (s.evDone) cudaEventDestroy(s.evDone);
+  if (s.evT0) cudaEventDestroy(s.evT0);
+  if (s.evT1) cudaEventDestroy(s.evT1);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
 }
@@ -239,6 +242,8 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   s.capKc = 0;
   CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming));
+  CK(cudaEventCreate(&s.evT0));
+  CK(cudaEventCreate(&s.evT1));
   const size_t np = (size_t)s.capPts, ns = (size_t)s.capScans;
   if (ownPoints) CK(dalloc(&s.d_pts, np));
   CK(dalloc(&s.d_surf, np)); CK(dalloc(&s.d_crop, np)); CK(dalloc(&s.d_sorted, np));
@@ -735,6 +740,7 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int
     if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
     for (int i = 0; i <= n_scans; i++) ctx->kpOffsets[i] = s.h_kpOff[i];
     collect_times(ctx, s);
+    s.nscans = n_scans; s.npts = npts; s.lastNch = nch;
   }
   out->n_scans = n_scans;
   out->n_keypoints = ctx->kpOffsets[n_scans];
@@ -743,6 +749,54 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int
   out->descriptors = desc ? s.d_desc : nullptr;
   out->on_device = 1;
   out->gpu_launches = ctx->launches - launches0;
+  return FE_OK;
+}
+
+int fe_timer_begin(fe_ctx_t* ctx) {
+  if (!ctx) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int st = ensure_slot(ctx, ctx->slot[0], false);
+  if (st) return st;
+  CK(cudaEventRecord(ctx->slot[0].evT0, ctx->slot[0].stream));
+  return FE_OK;
+}
+
+int fe_timer_end(fe_ctx_t* ctx, float* elapsed_ms) {
+  if (!ctx || !elapsed_ms || !ctx->slot[0].stream) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->slot[0].evT1, ctx->slot[0].stream));
+  CK(cudaEventSynchronize(ctx->slot[0].evT1));
+  CK(cudaEventElapsedTime(elapsed_ms, ctx->slot[0].evT0, ctx->slot[0].evT1));
+  return FE_OK;
+}
+
+int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[8]) {
+  if (!ctx || !out || !ctx->slot[0].stream) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[0];
+  CK(cudaStreamSynchronize(s.stream));
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  out[0] = s.npts;
+  std::vector<int> a((size_t)std::max(s.lastNch, 1)), b((size_t)std::max(s.lastNch, 1));
+  if (s.lastNch > 0) {
+    CK(cudaMemcpy(a.data(), s.d_surfCnt, (size_t)s.lastNch * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), s.d_cropCnt, (size_t)s.lastNch * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < s.lastNch; i++) { out[1] += a[i]; out[2] += b[i]; }
+  }
+  if (s.nscans > 0) {
+    std::vector<int> kf((size_t)s.nscans * 16);
+    CK(cudaMemcpy(kf.data(), s.d_kfCnt, kf.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int v : kf) out[3] += v;
+    const int K = s.h_kpOff[s.nscans];
+    out[4] = K;
+    if (K > 0 && ctx->params.estimate_descriptors) {
+      std::vector<int> nb((size_t)K);
+      CK(cudaMemcpy(nb.data(), s.d_kpNbr, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost));
+      for (int v : nb) out[5] += v;
+    }
+  }
+  out[6] = s.h_ctr->ovf_rings;
+  out[7] = s.h_ctr->ovf_merge;
   return FE_OK;
 }
 

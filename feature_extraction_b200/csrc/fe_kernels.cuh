@@ -73,6 +73,49 @@ struct DevCounters {
   int pad[1];
 };
 
+// getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
+__device__ __noinline__ float elevation_deg_literal(float xf, float yf, float zf) {
+  const double x = xf, y = yf, z = zf;
+  const double az = atan2(y, x);
+  double sn, cs;
+  sincos(az, &sn, &cs);
+  const double xp = __dadd_rn(__dmul_rn(cs, x), __dmul_rn(sn, y));
+  const double eld = __ddiv_rn(__dmul_rn(atan2(z, xp), 180.0), 3.14159265358979323846);
+  return (float)eld;
+}
+
+// The same value for the common case without the four double transcendentals.
+// cos(atan2(y,x))*x + sin(atan2(y,x))*y is hypot(x,y) up to a few double ulps (the expression is
+// stationary in the azimuth), so el = atan(z / hypot(x,y)) in degrees.  For |tan el| < 0.3 (|el| <
+// 16.7 deg: every VLP-16 beam) atan is a degree-8 polynomial in q^2 (|error| < 2^-53, fitted at
+// Chebyshev nodes).  The result is accepted only if every double within 2^-44 relative of it rounds
+// to the same float, i.e. the float the reference's double evaluation produces is not in doubt;
+// otherwise (about 1 point in 10^5) the literal evaluation above is used.
+__device__ __forceinline__ float elevation_deg(float xf, float yf, float zf) {
+  const double x = xf, y = yf, z = zf;
+  const double r2 = fma(x, x, y * y);
+  if (r2 > 1e-280 && r2 < 1e280) {
+    const double q = z * rsqrt(r2);
+    if (fabs(q) < 0.2999) {
+      const double u = q * q;
+      double p = 0.0414062517093382;
+      p = fma(p, u, -0.06392744183152536);
+      p = fma(p, u, 0.07668228432867163);
+      p = fma(p, u, -0.09089657177886407);
+      p = fma(p, u, 0.11111072588438455);
+      p = fma(p, u, -0.1428571361686184);
+      p = fma(p, u, 0.199999999941651);
+      p = fma(p, u, -0.3333333333331369);
+      p = fma(p, u, 0.9999999999999999);
+      const double deg = (q * p) * 57.295779513082320877;
+      const double eb = fabs(deg) * 5.6843418860808015e-14;  // 2^-44
+      const float lo = (float)(deg - eb), hi = (float)(deg + eb);
+      if (lo == hi) return lo;
+    }
+  }
+  return elevation_deg_literal(xf, yf, zf);
+}
+
 // ============================================================================================
 // K1 — fused elevation / level / crop / ring-bucket, order-preserving compaction per chunk.
 // Block = one chunk of CH consecutive points of one scan; 256 threads; warp w owns points
@@ -118,16 +161,7 @@ __global__ void __launch_bounds__(256) k_level_crop_ring(
     if (j < nIn) {
       const float4 p = __ldg(pts + base + j);
       float el = p.w;
-      if (flags & F_ELEV) {
-        // getElevationAngles, src:147-156 — double throughout
-        const double x = p.x, y = p.y, z = p.z;
-        const double az = atan2(y, x);
-        double sn, cs;
-        sincos(az, &sn, &cs);
-        const double xp = __dadd_rn(__dmul_rn(cs, x), __dmul_rn(sn, y));
-        const double eld = __ddiv_rn(__dmul_rn(atan2(z, xp), 180.0), 3.14159265358979323846);
-        el = (float)eld;
-      }
+      if (flags & F_ELEV) el = elevation_deg(p.x, p.y, p.z);  // getElevationAngles, src:147-156
       if (flags & F_ROT) {
         // pcl::transformPointCloud, PCL 1.8.0 scalar form: left to right, unfused, + translation 0
         q.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], p.x), __fmul_rn(m[1], p.y)), __fmul_rn(m[2], p.z)), 0.0f);
@@ -289,13 +323,20 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
     bb[tid] = v;
   }
   __syncthreads();
-  // cell slightly larger than the tolerance so that linked points are always in adjacent cells
-  // despite the rounding of the cell computation; indices clamp (monotone map keeps adjacency)
-  const float inv = 1.0f / (tol_f * 1.002f);
+  // Grid cell = 0.55 * tolerance.  Two properties follow, both with several percent of slack
+  // against the float rounding of the cell computation and of the d2 predicate:
+  //   (i)  two points in the same cell are closer than sqrt(3)*0.55*tol = 0.953*tol: they are
+  //        linked by construction and need no distance test;
+  //   (ii) two linked points (d < tol) are at most 2 cells apart on every axis.
+  // Cell indices clamp to the key's bit budget (x,y: 10 bits, z: 8 bits); the monotone clamp keeps
+  // (ii), but merges far cells, so (i) is only trusted when nothing had to be clamped.
+  const float inv = 1.0f / (tol_f * 0.55f);
   const float ox = bb[0], oy = bb[1], oz = bb[2];
-  const int nx = min(1024, (int)fminf(1023.0f, floorf((bb[3] - ox) * inv)) + 1);
-  const int ny = min(1024, (int)fminf(1023.0f, floorf((bb[4] - oy) * inv)) + 1);
-  const int nz = min(256, (int)fminf(255.0f, floorf((bb[5] - oz) * inv)) + 1);
+  const float fx = floorf((bb[3] - ox) * inv), fy = floorf((bb[4] - oy) * inv), fz = floorf((bb[5] - oz) * inv);
+  const bool trusted = (fx < 1023.0f) && (fy < 1023.0f) && (fz < 255.0f);
+  const int nx = (int)fminf(1023.0f, fmaxf(fx, 0.0f)) + 1;
+  const int ny = (int)fminf(1023.0f, fmaxf(fy, 0.0f)) + 1;
+  const int nz = (int)fminf(255.0f, fmaxf(fz, 0.0f)) + 1;
   const int bx = bits_for(nx - 1), by = bits_for(ny - 1), bz = bits_for(nz - 1);
   const int br = bits_for(nRings - 1);
   const int keybits = bx + by + bz + br;
@@ -317,47 +358,108 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
     kS = ko; kT = ki; vS = vo; vT = vi;
   }
   __syncthreads();
-  // ---- union-find over the neighbour cells ----
-  unsigned* parent = kT;
-  for (int e = tid; e < E; e += NT) parent[e] = (unsigned)e;
+  // ---- units: the runs of equal key (cells); every entry on its own when cells are not trusted ----
+  unsigned short* unitStart = S.lst;
+  int nU = 0;
+  {
+    int run = 0;
+    for (int p0 = 0; p0 < E; p0 += NT) {
+      const int p = p0 + tid;
+      const int head = (p < E && (!trusted || p == 0 || kS[p] != kS[p - 1])) ? 1 : 0;
+      int tot;
+      const int pos = block_excl_scan<NT>(head, &tot, sc);
+      if (head) unitStart[run + pos] = (unsigned short)p;
+      run += tot;
+    }
+    nU = run;
+  }
+  __syncthreads();
+  // ---- union-find over sorted positions; a cell's members start out linked to its first ----
+  unsigned* parentS = kT;
+  constexpr int G = 8;
+  const int gl = lane & (G - 1);
+  const unsigned gmask = 0xFFu << (lane & 24);
+  for (int u = tid / G; u < nU; u += NT / G) {
+    const int a0 = unitStart[u];
+    const int a1 = (u + 1 < nU) ? (int)unitStart[u + 1] : E;
+    for (int p = a0 + gl; p < a1; p += G) parentS[p] = (unsigned)a0;
+  }
   __syncthreads();
   const unsigned mxm = (1u << bx) - 1u, mym = (1u << by) - 1u, mzm = (1u << bz) - 1u;
-  for (int p = tid; p < E; p += NT) {
-    const unsigned key = kS[p];
-    const unsigned e = vS[p];
+  // One 8-lane group per unit.  The 13 rows (dz,dy) that precede the unit's own cell in key order
+  // and can hold linked points are located by 13 binary searches spread over the lanes; the
+  // candidates of a row are then visited 8 at a time.  A candidate already in the unit's component
+  // is skipped; otherwise it is tested against the unit's members until the first link.
+  for (int u = tid / G; u < nU; u += NT / G) {
+    const int a0 = unitStart[u];
+    const int a1 = (u + 1 < nU) ? (int)unitStart[u + 1] : E;
+    const unsigned key = kS[a0];
     const int cx = (int)(key & mxm), cy = (int)((key >> bx) & mym), cz = (int)((key >> (bx + by)) & mzm);
     const unsigned rg = key >> (bx + by + bz);
-    const float px = S.x[e], py = S.y[e], pz = S.z[e];
-    for (int dz = -1; dz <= 0; dz++) {
-      const int zz = cz + dz;
-      if (zz < 0) continue;
-      const int dyhi = (dz == 0) ? 0 : 1;
-      for (int dy = -1; dy <= dyhi; dy++) {
-        const int yy = cy + dy;
-        if (yy < 0 || yy >= ny) continue;
-        const unsigned rowk = (((rg << bz) | (unsigned)zz) << by | (unsigned)yy) << bx;
-        const unsigned klo = rowk | (unsigned)max(cx - 1, 0);
-        const unsigned khi = rowk | (unsigned)min(cx + 1, nx - 1);
-        const bool own = (dz == 0 && dy == 0);
-        int lo = 0, hi = own ? p : E;  // lower_bound(klo) in kS[0, hi)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (kS[mid] < klo) lo = mid + 1; else hi = mid;
+    int lo[2] = {0, 0}, end[2] = {0, 0};
+    unsigned khi[2] = {0u, 0u};
+#pragma unroll
+    for (int rnd = 0; rnd < 2; rnd++) {
+      const int r = gl + 8 * rnd;  // 0..9: dz=-2,-1 x dy=-2..2; 10,11: dz=0, dy=-2,-1; 12: own row
+      if (r < 13) {
+        const int dz = (r < 5) ? -2 : (r < 10) ? -1 : 0;
+        const int dy = (r < 10) ? (r % 5) - 2 : (r == 12) ? 0 : r - 12;
+        const int zz = cz + dz, yy = cy + dy;
+        if (zz >= 0 && yy >= 0 && yy < ny) {
+          const unsigned rowk = (((rg << bz) | (unsigned)zz) << by | (unsigned)yy) << bx;
+          const unsigned klo = rowk | (unsigned)max(cx - 2, 0);
+          khi[rnd] = rowk | (unsigned)min(cx + 2, nx - 1);
+          end[rnd] = (r == 12) ? a0 : E;
+          int l = 0, h = end[rnd];  // lower_bound(klo) in kS[0, end)
+          while (l < h) {
+            const int mid = (l + h) >> 1;
+            if (kS[mid] < klo) l = mid + 1; else h = mid;
+          }
+          lo[rnd] = l;
         }
-        const int end = own ? p : E;
-        for (int q = lo; q < end; q++) {
-          if (kS[q] > khi) break;
+      }
+    }
+#pragma unroll 1
+    for (int r = 0; r < 13; r++) {
+      const int src = r & 7;
+      const int rlo = __shfl_sync(gmask, (r < 8) ? lo[0] : lo[1], src, G);
+      const int rend = __shfl_sync(gmask, (r < 8) ? end[0] : end[1], src, G);
+      const unsigned rkhi = __shfl_sync(gmask, (r < 8) ? khi[0] : khi[1], src, G);
+      for (int q0 = rlo; q0 < rend; q0 += G) {
+        const int q = q0 + gl;
+        const bool in = (q < rend) && (kS[q] <= rkhi);
+        if (in && uf_find(parentS, (unsigned)q) != uf_find(parentS, (unsigned)a0)) {
           const unsigned e2 = vS[q];
-          const float d2 = l2_simple(px, py, pz, S.x[e2], S.y[e2], S.z[e2]);
-          if (d2 < r2f) uf_union(parent, e, e2);
+          const float qx = S.x[e2], qy = S.y[e2], qz = S.z[e2];
+          for (int a = a0; a < a1; a++) {
+            const unsigned ea = vS[a];
+            if (l2_simple(S.x[ea], S.y[ea], S.z[ea], qx, qy, qz) < r2f) {
+              uf_union(parentS, (unsigned)a0, (unsigned)q);
+              break;
+            }
+          }
         }
+        if (!__shfl_sync(gmask, (int)in, G - 1, G)) break;  // keys are sorted: nothing further in range
       }
     }
   }
   __syncthreads();
-  // ---- flatten, component sizes ----
+  // ---- flatten; label every component with its smallest entry (= its first point in the cloud) ----
+  for (int p = tid; p < E; p += NT) parentS[p] = uf_find_readonly(parentS, (unsigned)p);
+  __syncthreads();
+  unsigned* minE = kS;
+  for (int p = tid; p < E; p += NT) minE[p] = 0xFFFFFFFFu;
+  __syncthreads();
+  for (int p = tid; p < E; p += NT) atomicMin(&minE[parentS[p]], (unsigned)vS[p]);
+  __syncthreads();
+  for (int p = tid; p < E; p += NT) {
+    vT[p] = (unsigned short)minE[parentS[p]];
+    S.aux[vS[p]] = (unsigned short)p;
+  }
+  __syncthreads();
+  unsigned* parent = kT;  // from here on indexed by entry: parent[e] = first entry of e's component
   unsigned* cnt = kS;
-  for (int e = tid; e < E; e += NT) { parent[e] = uf_find_readonly(parent, (unsigned)e); cnt[e] = 0; }
+  for (int e = tid; e < E; e += NT) { parent[e] = vT[S.aux[e]]; cnt[e] = 0; }
   __syncthreads();
   for (int e = tid; e < E; e += NT) atomicAdd(&cnt[parent[e]], 1u);
   __syncthreads();

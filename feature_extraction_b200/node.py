@@ -255,6 +255,21 @@ class FeatureExtractionNode:
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, 4)).copy()
         return co, arr(cp, int(co[-1])), kco, arr(kcp, int(kco[-1]))
 
+    def timerBegin(self):
+        self._check(N.lib().fe_timer_begin(self._ctx))
+
+    def timerEnd(self):
+        ms = C.c_float(0)
+        self._check(N.lib().fe_timer_end(self._ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def batchStats(self):
+        out = np.zeros(8, np.int64)
+        self._check(N.lib().fe_get_batch_stats(self._ctx, _ptr(out)))
+        keys = ("points", "surface_points", "crop_points", "ring_clusters", "keypoints", "neighbours",
+                "deferred_ring_scans", "deferred_merge_scans")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def stageTimes(self):
         names = (C.c_char_p * 32)()
         ms = (C.c_float * 32)()

@@ -124,6 +124,16 @@ int fe_enable_cloud_outputs(fe_ctx_t* ctx, int32_t enable);
 int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_point_t** cloud,
                          const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud);
 
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of
+ * fe_process_batch_device is launched on): begin, run any number of calls, end -> elapsed ms. */
+int fe_timer_begin(fe_ctx_t* ctx);
+int fe_timer_end(fe_ctx_t* ctx, float* elapsed_ms);
+
+/* Work counters of the last fe_process_batch_device call (for roofline arithmetic):
+ * out[0..7] = points, surface points kept, cropped points, ring clusters (keypoints_full),
+ * keypoints, sum of 3DSC neighbours, scans deferred to the large K2, scans deferred to the large K3. */
+int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[8]);
+
 /* Per-kernel CUDA-event times (ms) of the last device call; names are static strings. */
 int fe_get_stage_times(fe_ctx_t* ctx, int32_t cap, const char** names, float* ms, int32_t* n);
 

@@ -149,3 +149,31 @@ def test_full_batch_size_properties(ob, synth):
     for i, s in enumerate(sel):
         assert bits_equal(kp_c[ko_c[i]:ko_c[i + 1]], kp_a[ko_a[s]:ko_a[s + 1]])
     b.close()
+
+
+def test_elevation_fast_path_rounds_like_the_double_evaluation(ob, node):
+    """Row A on 3M points: sensor-like geometry plus arbitrary directions and magnitudes.  The fast
+    path accepts a value only when its float rounding is not in doubt, so the result must equal the
+    oracle's double evaluation bit for bit (a 1-ulp difference is possible only through libm's own
+    double rounding, ~1e-8 per point: at most a couple of points here)."""
+    rng = np.random.default_rng(42)
+    n = 1_000_000
+    az = rng.uniform(-np.pi, np.pi, n)
+    el = np.deg2rad(rng.choice(np.arange(-15, 16, 2), n) + rng.normal(0, 0.05, n))
+    r = rng.uniform(0.5, 100.0, n)
+    a = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el), np.zeros(n)], 1)
+    b = rng.normal(0, 1, (n, 4)) * np.exp(rng.uniform(-20, 20, (n, 1)))       # any direction, any scale
+    c = rng.normal(0, 30, (n, 4))
+    c[:1000, 0] = 0.0                                                          # on the axes
+    c[1000:2000, 1] = 0.0
+    c[2000:3000, 2] = 0.0
+    c[3000:3100, :2] = 0.0
+    pts = np.concatenate([a, b, c]).astype(np.float32)
+    pts[:, 3] = 0
+    g = node.getElevationAngles(pts)
+    o = ob.get_elevation_angles(pts)
+    diff = np.flatnonzero(g[:, 3].view(np.uint32) != o[:, 3].view(np.uint32))
+    assert len(diff) <= 3, (len(diff), g[diff[:5]], o[diff[:5]])
+    if len(diff):
+        assert np.all(np.abs(g[diff, 3] - o[diff, 3]) <= np.spacing(np.abs(o[diff, 3])))
+    assert bits_equal(g[:, :3], pts[:, :3])
