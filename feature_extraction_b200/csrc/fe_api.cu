@@ -337,14 +337,14 @@ int ensure_kc(fe_ctx* ctx, Slot& s) {
   return FE_OK;
 }
 
-const size_t kClusterSmem = cluster_smem_bytes(ECAP);
-const size_t kClusterSmemL = cluster_smem_bytes(ECAP_L);
+const size_t kClusterSmem = cluster_smem_bytes(ECAP, NTF);
+const size_t kClusterSmemL = cluster_smem_bytes(ECAP_L, NT2);
 
 int set_kernel_attrs(fe_ctx* ctx) {
-  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
-  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP, NTF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   return FE_OK;
 }
@@ -359,17 +359,17 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
   float4* kc = wantKc ? s.d_kcPool : nullptr;
   int* kcB = wantKc ? s.d_kcBase : nullptr;
   int* kcC = wantKc ? s.d_kcCnt : nullptr;
-  k_cluster_rings<ECAP, 2><<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
+  k_cluster_rings<ECAP, NTF, 4><<<nscans, NTF, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
                                                                     singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
                                                                     s.capKc, kcB, kcC, s.d_ctr, nullptr, nullptr, s.d_ovfRings);
-  k_cluster_rings<ECAP_L, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
+  k_cluster_rings<ECAP_L, NT2, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
                                                                       singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
                                                                       s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr);
   ctx->launches += 2;
   if (merge) {
-    k_merge_keypoints<ECAP, 2><<<nscans, NT2, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
+    k_merge_keypoints<ECAP, NTF, 4><<<nscans, NTF, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
                                                                         s.d_kpBase, s.d_kpCnt, s.d_ctr, nullptr, nullptr, s.d_ovfMerge);
-    k_merge_keypoints<ECAP_L, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
+    k_merge_keypoints<ECAP_L, NT2, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
                                                                           s.d_kpBase, s.d_kpCnt, s.d_ctr, s.d_ovfMerge, ovfM, nullptr);
     ctx->launches += 2;
   }

@@ -22,10 +22,11 @@
 namespace fe {
 
 constexpr int CH = 2048;        // points per K1 chunk (one block)
-constexpr int MAXCHUNK = 1024;  // chunks per scan the per-scan kernels can index (2M points)
+constexpr int MAXCHUNK = 512;   // chunks per scan the per-scan kernels can index (1M points)
 constexpr int NT2 = 512;        // threads of the per-scan clustering / grid kernels
-constexpr int ECAP = 2944;      // cluster entries a block holds in shared memory (2 blocks / SM)
-constexpr int ECAP_L = 6528;    // the large instantiation (1 block / SM) for scans the fast one defers
+constexpr int ECAP = 1408;      // cluster entries of the fast instantiation (256 threads, 4 blocks / SM)
+constexpr int NTF = 256;
+constexpr int ECAP_L = 6528;    // the large instantiation (512 threads, 1 block / SM) for scans the fast one defers
 
 // error bits reported through DevCounters::err
 enum {
@@ -248,16 +249,16 @@ struct ClusterSm {
   unsigned char* ring;
   unsigned *keyA, *keyB;
   unsigned short *valA, *valB, *aux, *lst;
-  unsigned short* wc;      // NT2/32 * 257
+  unsigned short* wc;      // NT/32 * 257
   unsigned* base;          // 256 + 32
   int* misc;               // MISC_INTS
 };
 constexpr int MISC_INTS = MAXCHUNK + 1 + 128;
-constexpr size_t cluster_smem_bytes(int cap) {
-  return (size_t)cap * (12 + 4 + 1 + 8 + 8) + (NT2 / 32) * 257 * 2 + (256 + 32) * 4 + MISC_INTS * 4 + 64;
+constexpr size_t cluster_smem_bytes(int cap, int nt) {
+  return (size_t)cap * (12 + 4 + 1 + 8 + 8) + (nt / 32) * 257 * 2 + (256 + 32) * 4 + MISC_INTS * 4 + 64;
 }
 
-template <int CAP>
+template <int CAP, int NT>
 __device__ __forceinline__ void cluster_sm_carve(unsigned char* p, ClusterSm& S) {
   S.x = (float*)p; p += CAP * 4;
   S.y = (float*)p; p += CAP * 4;
@@ -271,7 +272,7 @@ __device__ __forceinline__ void cluster_sm_carve(unsigned char* p, ClusterSm& S)
   S.valB = (unsigned short*)p; p += CAP * 2;
   S.aux = (unsigned short*)p; p += CAP * 2;
   S.lst = (unsigned short*)p; p += CAP * 2;
-  S.wc = (unsigned short*)p; p += (NT2 / 32) * 257 * 2;
+  S.wc = (unsigned short*)p; p += (NT / 32) * 257 * 2;
   S.ring = (unsigned char*)p;
 }
 
@@ -495,20 +496,16 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
     if (tid < 16) ringEnd[tid] = nC;
   }
   __syncthreads();
-  if (lane == 0 && w < nRings) {
-    const int b = (w == 0) ? 0 : ringEnd[w - 1];
-    const int n = ringEnd[w] - b;
-    if (n > 1) {
-      const unsigned* c2 = cnt;
-      pcl_cluster_order(S.lst + b, n, [=](unsigned short id) { return c2[id]; });
-    }
-  }
-  if (nRings > NT / 32 && tid == 0) {  // not reachable with 16 rings and 16 warps; kept for safety
-    for (int r = NT / 32; r < nRings; r++) {
-      const int b = ringEnd[r - 1];
+  {
+    constexpr int STRIDE = NT / 16;  // one thread per ring, spread over the warps
+    if ((tid % STRIDE) == 0 && (tid / STRIDE) < nRings) {
+      const int r = tid / STRIDE;
+      const int b = (r == 0) ? 0 : ringEnd[r - 1];
       const int n = ringEnd[r] - b;
-      const unsigned* c2 = cnt;
-      if (n > 1) pcl_cluster_order(S.lst + b, n, [=](unsigned short id) { return c2[id]; });
+      if (n > 1) {
+        const unsigned* c2 = cnt;
+        pcl_cluster_order(S.lst + b, n, [=](unsigned short id) { return c2[id]; });
+      }
     }
   }
   for (int e = tid; e < E; e += NT) S.aux[e] = 0xFFFFu;
@@ -581,7 +578,7 @@ __device__ __forceinline__ long long piece_pos(const int* pre, int nch, int i, l
 // ============================================================================================
 // K2 — per-ring clustering and getCylinderSegments gating for one scan per block.
 // ============================================================================================
-template <int CAP>
+template <int CAP, int NT>
 __device__ void cluster_rings_scan(
     ClusterSm& S, const int s, const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta,
     const int* __restrict__ cropCnt, const long long* __restrict__ scan_off,
@@ -597,12 +594,12 @@ __device__ void cluster_rings_scan(
   const int nch = chunk_off[s + 1] - chunk_off[s];
   if (tid < 16) { kfBase[s * 16 + tid] = 0; kfCnt[s * 16 + tid] = 0; if (kcBase) { kcBase[s * 16 + tid] = 0; kcCnt[s * 16 + tid] = 0; } }
   if (nch > MAXCHUNK) { if (tid == 0) atomicOr(&ctr->err, ERR_CHUNKS); return; }
-  const int Nc = chunk_prefix<NT2>(cropCnt + chunk_off[s], nch, pre, sc);
+  const int Nc = chunk_prefix<NT>(cropCnt + chunk_off[s], nch, pre, sc);
   if (Nc == 0) return;
   // entries per ring
   if (tid < 16) ringCnt[tid] = 0;
   __syncthreads();
-  for (int i = tid; i < Nc; i += NT2) {
+  for (int i = tid; i < Nc; i += NT) {
     const unsigned cd = cropMeta[piece_pos(pre, nch, i, base)] & 63u;
     if (cd & 32u) continue;
     const int r = single_ring ? 0 : (int)(cd & 15u);
@@ -631,7 +628,7 @@ __device__ void cluster_rings_scan(
     if (tot > 0) {
       // ---- gather the entries of rings [r0, r1) in original order ----
       int run = 0;
-      for (int i0 = 0; i0 < Nc; i0 += NT2) {
+      for (int i0 = 0; i0 < Nc; i0 += NT) {
         const int i = i0 + tid;
         int take = 0, ra = 0, rb = -1;
         long long pp = 0;
@@ -648,7 +645,7 @@ __device__ void cluster_rings_scan(
           }
         }
         int t2;
-        const int pos = block_excl_scan<NT2>(take, &t2, sc);
+        const int pos = block_excl_scan<NT>(take, &t2, sc);
         if (take) {
           const float4 q = crop[pp];
           int e = run + pos;
@@ -663,14 +660,14 @@ __device__ void cluster_rings_scan(
       __syncthreads();
       const int E = run;
       ClusterOut C;
-      cluster_extract<NT2>(S, E, P.tol_f, P.r2f_cluster, P.min_count, P.max_count, r1 - r0, C);
+      cluster_extract<NT>(S, E, P.tol_f, P.r2f_cluster, P.min_count, P.max_count, r1 - r0, C);
       // ---- getCylinderSegments gate + centroid per cluster (src:282-325), one thread each ----
       int* sh = sc + 100;  // [0] = pool base, [1] = kc base
       int runG = 0, runM = 0;
       // pass 1 counts, pass 2 writes; the per-cluster result is cached in registers per tile
       for (int pass = 0; pass < 2; pass++) {
         int accG = 0, accM = 0;
-        for (int i0 = 0; i0 < C.nC; i0 += NT2) {
+        for (int i0 = 0; i0 < C.nC; i0 += NT) {
           const int i = i0 + tid;
           int ok = 0, size = 0;
           float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -700,9 +697,9 @@ __device__ void cluster_rings_scan(
             }
           }
           int tg, tm;
-          const int pg = block_excl_scan<NT2>(ok, &tg, sc);
+          const int pg = block_excl_scan<NT>(ok, &tg, sc);
           int pm = 0;
-          if (kcPool) pm = block_excl_scan<NT2>(ok ? size : 0, &tm, sc); else tm = 0;
+          if (kcPool) pm = block_excl_scan<NT>(ok ? size : 0, &tm, sc); else tm = 0;
           if (pass == 1 && ok) {
             const int b = sh[0];
             if (b >= 0) kfPool[b + accG + pg] = cen;
@@ -746,8 +743,8 @@ __device__ void cluster_rings_scan(
 
 // scanList == nullptr: block b handles scan b and defers oversized scans to ovfList;
 // otherwise the blocks loop over scanList[0 .. *nList) (the deferred scans).
-template <int CAP, int MINB>
-__global__ void __launch_bounds__(NT2, MINB) k_cluster_rings(
+template <int CAP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_cluster_rings(
     const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta,
     const int* __restrict__ cropCnt, const long long* __restrict__ scan_off,
     const int* __restrict__ chunk_off, DevParams P, int single_ring,
@@ -757,15 +754,15 @@ __global__ void __launch_bounds__(NT2, MINB) k_cluster_rings(
     int* __restrict__ ovfList) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
-  cluster_sm_carve<CAP>(smem_raw, S);
+  cluster_sm_carve<CAP, NT>(smem_raw, S);
   if (!scanList) {
-    cluster_rings_scan<CAP>(S, blockIdx.x, crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
+    cluster_rings_scan<CAP, NT>(S, blockIdx.x, crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
                             kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfList);
   } else {
     const int n = *nList;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
       __syncthreads();
-      cluster_rings_scan<CAP>(S, scanList[i], crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
+      cluster_rings_scan<CAP, NT>(S, scanList[i], crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
                               kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, nullptr);
     }
   }
@@ -775,7 +772,7 @@ __global__ void __launch_bounds__(NT2, MINB) k_cluster_rings(
 // K3 — cross-ring merge (src:205-257) for one scan per block; also the stage kernel behind
 // fe_extract_clusters when `stage` != 0 (then it just reports the clusters of `crop`).
 // ============================================================================================
-template <int CAP>
+template <int CAP, int NT>
 __device__ void merge_keypoints_scan(
     ClusterSm& S, const int s, const float4* __restrict__ kfPool, const int* __restrict__ kfBase,
     const int* __restrict__ kfCnt, const DevParams& P, float4* __restrict__ kpPool, int kpCap,
@@ -800,7 +797,7 @@ __device__ void merge_keypoints_scan(
     }
     return;
   }
-  for (int i = tid; i < Kf; i += NT2) {
+  for (int i = tid; i < Kf; i += NT) {
     int g = 0;
     while (g < 15 && pre[g + 1] <= i) g++;
     const int src = kfBase[s * 16 + g] + (i - pre[g]);
@@ -813,7 +810,7 @@ __device__ void merge_keypoints_scan(
   }
   __syncthreads();
   ClusterOut C;
-  cluster_extract<NT2>(S, Kf, P.merge_tol_f, P.r2f_merge, P.min_channels, 16, 1, C);
+  cluster_extract<NT>(S, Kf, P.merge_tol_f, P.r2f_merge, P.min_channels, 16, 1, C);
   if (C.nC == 0) return;
   int* sh = sc + 100;
   if (tid == 0) {
@@ -826,7 +823,7 @@ __device__ void merge_keypoints_scan(
   __syncthreads();
   const int b = sh[0];
   if (b < 0) return;
-  for (int i = tid; i < C.nC; i += NT2) {
+  for (int i = tid; i < C.nC; i += NT) {
     const unsigned root = C.slotRoot[i];
     const int size = (int)C.cnt[root];
     const int st = C.slotStart[i];
@@ -846,22 +843,22 @@ __device__ void merge_keypoints_scan(
   }
 }
 
-template <int CAP, int MINB>
-__global__ void __launch_bounds__(NT2, MINB) k_merge_keypoints(
+template <int CAP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_merge_keypoints(
     const float4* __restrict__ kfPool, const int* __restrict__ kfBase, const int* __restrict__ kfCnt,
     DevParams P, float4* __restrict__ kpPool, int kpCap, int* __restrict__ kpBase,
     int* __restrict__ kpCnt, DevCounters* __restrict__ ctr, const int* __restrict__ scanList,
     const int* __restrict__ nList, int* __restrict__ ovfList) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
-  cluster_sm_carve<CAP>(smem_raw, S);
+  cluster_sm_carve<CAP, NT>(smem_raw, S);
   if (!scanList) {
-    merge_keypoints_scan<CAP>(S, blockIdx.x, kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, ovfList);
+    merge_keypoints_scan<CAP, NT>(S, blockIdx.x, kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, ovfList);
   } else {
     const int n = *nList;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
       __syncthreads();
-      merge_keypoints_scan<CAP>(S, scanList[i], kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, nullptr);
+      merge_keypoints_scan<CAP, NT>(S, scanList[i], kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, nullptr);
     }
   }
 }
@@ -872,7 +869,7 @@ __global__ void __launch_bounds__(NT2, 1) k_extract_clusters_stage(
     int* __restrict__ offsets, int capClusters, int* __restrict__ indices, int* __restrict__ nOut) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
-  cluster_sm_carve<ECAP_L>(smem_raw, S);
+  cluster_sm_carve<ECAP_L, NT2>(smem_raw, S);
   const int tid = threadIdx.x;
   for (int i = tid; i < n; i += NT2) {
     const float4 q = pts[i];

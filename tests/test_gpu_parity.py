@@ -132,3 +132,14 @@ def test_device_resident_entry_point_equals_host_entry_point(ob, synth, nodes):
     d2 = nd.download(p_d, (K, 1980))
     from util import rel_err
     assert rel_err(d2, d).max() < 1e-5
+
+
+def test_cpp_host_mirror_example_runs():
+    """The C++ FeatureExtractionCore (reference method names) stage-by-stage == fused, on the GPU."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    out = subprocess.run([os.path.join(root, "examples", "core_example")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "identical" in out.stdout and "1 keypoints" in out.stdout

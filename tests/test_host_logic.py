@@ -106,3 +106,11 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_binding" not in txt and "libfe_oracle" not in txt and "fe_oracle" not in txt, (dp, f)
+
+
+def test_cpp_host_mirror_builds_against_the_c_abi():
+    """include/feature_extraction_b200/feature_extraction_core.hpp + examples/core_example.cpp compile
+    and link with nothing but the C-ABI (no CUDA, PCL or ROS headers)."""
+    import subprocess
+    subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "examples")])
+    assert os.path.exists(os.path.join(ROOT, "examples", "core_example"))
