@@ -33,7 +33,7 @@ struct Slot {
   int *d_kfBase = nullptr, *d_kfCnt = nullptr, *d_kcBase = nullptr, *d_kcCnt = nullptr;
   int *d_kpBase = nullptr, *d_kpCnt = nullptr, *d_kpOff = nullptr, *d_kpScan = nullptr, *d_kpNbr = nullptr;
   int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
-  int *d_ovfRings = nullptr, *d_ovfMerge = nullptr;
+  int *d_ovfRings = nullptr, *d_ovfMerge = nullptr, *d_ovfSurf = nullptr;
   int64_t capRowStart = 0;
   float4 *d_kfPool = nullptr, *d_kcPool = nullptr, *d_kpPool = nullptr, *d_kpOut = nullptr, *d_gather = nullptr;
   float* d_desc = nullptr;
@@ -216,7 +216,7 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfMerge, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfMerge, s.d_ovfSurf, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
   for (void* p : hv) if (p) cudaFreeHost(p);
@@ -258,7 +258,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_kpBase, ns)); CK(dalloc(&s.d_kpCnt, ns)); CK(dalloc(&s.d_kpOff, ns + 1));
   CK(dalloc(&s.d_kpScan, (size_t)s.capKp)); CK(dalloc(&s.d_kpNbr, (size_t)s.capKp));
   CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1));
-  CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfMerge, ns));
+  CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfSurf, ns));
   CK(dalloc(&s.d_kfPool, (size_t)s.capKf)); CK(dalloc(&s.d_kpPool, (size_t)s.capKp)); CK(dalloc(&s.d_kpOut, (size_t)s.capKp));
   CK(dalloc(&s.d_desc, (size_t)s.capKp * FE_DESC_LEN));
   CK(dalloc(&s.d_ctr, 1));
@@ -339,14 +339,34 @@ int ensure_kc(fe_ctx* ctx, Slot& s) {
 
 const size_t kClusterSmem = cluster_smem_bytes(ECAP, NTF);
 const size_t kClusterSmemL = cluster_smem_bytes(ECAP_L, NT2);
+const size_t kClusterSmemM = cluster_smem_bytes(ECAP_M, NTM);
 
 int set_kernel_attrs(fe_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP, NTF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_surface_grid_smem<unsigned short, SCAP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)surf_smem_bytes(SCAP16, 2)));
+  CK(cudaFuncSetAttribute(k_surface_grid_smem<unsigned, SCAP32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)surf_smem_bytes(SCAP32, 4)));
   return FE_OK;
+}
+
+// K4a: shared-memory sort for scans that fit, global-memory sort for the deferred rest.
+void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
+  const int keybits = P.sg_bx + bits_for_host(P.sg_ny - 1);
+  if (keybits <= 16)
+    k_surface_grid_smem<unsigned short, SCAP16><<<nscans, NT2, surf_smem_bytes(SCAP16, 2), s.stream>>>(
+        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf);
+  else
+    k_surface_grid_smem<unsigned, SCAP32><<<nscans, NT2, surf_smem_bytes(SCAP32, 4), s.stream>>>(
+        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf);
+  k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB,
+                                                                 s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN,
+                                                                 s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf);
+  ctx->launches += 2;
 }
 
 // K2 + K3 for `nscans` scans: the 2-blocks-per-SM instantiation first, then the large one over
@@ -367,8 +387,9 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
                                                                       s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr);
   ctx->launches += 2;
   if (merge) {
-    k_merge_keypoints<ECAP, NTF, 4><<<nscans, NTF, kClusterSmem, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
-                                                                        s.d_kpBase, s.d_kpCnt, s.d_ctr, nullptr, nullptr, s.d_ovfMerge);
+    k_merge_keypoints<ECAP_M, NTM, 8><<<nscans, NTM, kClusterSmemM, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool,
+                                                                                (int)s.capKp, s.d_kpBase, s.d_kpCnt, s.d_ctr, nullptr,
+                                                                                nullptr, s.d_ovfMerge);
     k_merge_keypoints<ECAP_L, NT2, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
                                                                           s.d_kpBase, s.d_kpCnt, s.d_ctr, s.d_ovfMerge, ovfM, nullptr);
     ctx->launches += 2;
@@ -401,9 +422,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     int st = ensure_rowstart(ctx, s, nscans);
     if (st) return st;
     CK(cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(npts, 1) * sizeof(int), s.stream));
-    k_surface_grid<<<nscans, NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA,
-                                                 s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr);
-    ctx->launches++;
+    launch_surface_grid(ctx, s, nscans, P);
     mark(ctx, s, "K4a surface grid");
     const int gridKp = 148 * 8;
     k_desc_mark<<<gridKp, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, s.d_sortedKey, s.d_rowStart,
@@ -1022,8 +1041,7 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
       cudaMemcpyAsync(s.d_kpOut, keypoints, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, q) != cudaSuccess ||
       cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(int), q) != cudaSuccess)
     return restore(fail(ctx, FE_ERR_CUDA, "staging of the descriptor inputs failed"));
-  k_surface_grid<<<1, NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
-                                   s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr);
+  launch_surface_grid(ctx, s, 1, P);
   k_desc_mark<<<148 * 4, 256, 0, q>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, 1, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P,
                                       s.d_rho, s.d_kpNbr);
   if (n > 0) {
@@ -1033,7 +1051,7 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
   }
   k_desc_hist<<<148 * 4, 256, 0, q>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, 1, s.d_kpNbr, s.d_sorted, s.d_sortedKey, s.d_rowStart,
                                       s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_desc, s.d_ctr);
-  ctx->launches += 3;
+  ctx->launches += 2;
   ctx->dp = saved;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, q));

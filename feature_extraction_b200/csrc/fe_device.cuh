@@ -75,23 +75,44 @@ __device__ __forceinline__ void block_radix_pass(int n, DigitFn digit_of, MoveFn
   __syncthreads();
   for (int i = tid; i < n; i += NT) atomicAdd(&base[digit_of(i)], 1u);
   __syncthreads();
-  // exclusive scan of the 256 digit counts (warps 0..7)
-  unsigned v = 0, inc = 0;
-  if (tid < 256) {
-    v = base[tid];
-    inc = v;
+  // exclusive scan of the 256 digit counts
+  if constexpr (NT >= 256) {
+    unsigned v = 0, inc = 0;
+    if (tid < 256) {
+      v = base[tid];
+      inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned t = __shfl_up_sync(FE_FULL, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (lane == 31) wsum[w] = inc;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      unsigned off = 0;
+      for (int i = 0; i < w; i++) off += wsum[i];
+      base[tid] = off + inc - v;
+    }
+  } else {
+    constexpr int DPT = 256 / NT;  // consecutive digits per thread
+    unsigned loc[DPT];
+    unsigned sum = 0;
+#pragma unroll
+    for (int k = 0; k < DPT; k++) { loc[k] = base[tid * DPT + k]; sum += loc[k]; }
+    unsigned inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       unsigned t = __shfl_up_sync(FE_FULL, inc, d);
       if (lane >= d) inc += t;
     }
     if (lane == 31) wsum[w] = inc;
-  }
-  __syncthreads();
-  if (tid < 256) {
+    __syncthreads();
     unsigned off = 0;
     for (int i = 0; i < w; i++) off += wsum[i];
-    base[tid] = off + inc - v;
+    unsigned run = off + inc - sum;
+#pragma unroll
+    for (int k = 0; k < DPT; k++) { base[tid * DPT + k] = run; run += loc[k]; }
   }
   __syncthreads();
   for (int t0 = 0; t0 < n; t0 += TILE) {
@@ -115,14 +136,14 @@ __device__ __forceinline__ void block_radix_pass(int n, DigitFn digit_of, MoveFn
       __syncwarp();
     }
     __syncthreads();
-    if (tid < 256) {
-      unsigned run = base[tid];
+    for (int dd = tid; dd < 256; dd += NT) {
+      unsigned run = base[dd];
       for (int ww = 0; ww < NW; ww++) {
-        unsigned c = wc[ww * 257 + tid];
-        wc[ww * 257 + tid] = (CntT)run;
+        unsigned c = wc[ww * 257 + dd];
+        wc[ww * 257 + dd] = (CntT)run;
         run += c;
       }
-      base[tid] = run;
+      base[dd] = run;
     }
     __syncthreads();
 #pragma unroll

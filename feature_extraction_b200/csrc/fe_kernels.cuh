@@ -26,6 +26,8 @@ constexpr int MAXCHUNK = 512;   // chunks per scan the per-scan kernels can inde
 constexpr int NT2 = 512;        // threads of the per-scan clustering / grid kernels
 constexpr int ECAP = 1408;      // cluster entries of the fast instantiation (256 threads, 4 blocks / SM)
 constexpr int NTF = 256;
+constexpr int ECAP_M = 512;     // K3 fast instantiation: ring centroids per scan (64 threads, many blocks / SM)
+constexpr int NTM = 64;
 constexpr int ECAP_L = 6528;    // the large instantiation (512 threads, 1 block / SM) for scans the fast one defers
 
 // error bits reported through DevCounters::err
@@ -71,7 +73,7 @@ struct DevCounters {
   int kp_total;
   int ovf_rings;   // scans deferred from K2 to its large instantiation
   int ovf_merge;   // scans deferred from K3 to its large instantiation
-  int pad[1];
+  int ovf_surf;    // scans deferred from the shared-memory K4a to the global-memory one
 };
 
 // getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
@@ -124,7 +126,7 @@ __device__ __forceinline__ float elevation_deg(float xf, float yf, float zf) {
 // the chunk's own slot of the output arrays (same CSR as the input) with their counts, so the
 // per-scan consumers concatenate pieces in order and no global prefix sum is needed.
 // ============================================================================================
-__global__ void __launch_bounds__(256) k_level_crop_ring(
+__global__ void __launch_bounds__(256, 4) k_level_crop_ring(
     const float4* __restrict__ pts, const long long* __restrict__ scan_off,
     const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
     int flags, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
@@ -185,10 +187,12 @@ __global__ void __launch_bounds__(256) k_level_crop_ring(
           // ring i keeps (i-7)*2-1 +- 1 inclusive (src:200-202); windows share their end points
           rm = 0u;
           if (isfinite(el)) {
+            const int i0 = (int)floorf(fminf(fmaxf((el + 16.0f) * 0.5f, -2.0f), 18.0f));
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int d = -1; d <= 1; d++) {
+              const int i = i0 + d;
               const float lo = (float)(2 * i - 16), hi = (float)(2 * i - 14);
-              if (!(el < lo || el > hi)) rm |= 1u << i;
+              if (i >= 0 && i < 16 && !(el < lo || el > hi)) rm |= 1u << i;
             }
           }
         }
@@ -338,14 +342,15 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
   const int nx = (int)fminf(1023.0f, fmaxf(fx, 0.0f)) + 1;
   const int ny = (int)fminf(1023.0f, fmaxf(fy, 0.0f)) + 1;
   const int nz = (int)fminf(255.0f, fmaxf(fz, 0.0f)) + 1;
-  const int bx = bits_for(nx - 1), by = bits_for(ny - 1), bz = bits_for(nz - 1);
-  const int br = bits_for(nRings - 1);
-  const int keybits = bx + by + bz + br;
+  // key = ((ring*nz + cz)*ny + cy)*nx + cx  (< 2^32: 16 * 256 * 1024 * 1024)
+  const unsigned unx = (unsigned)nx, uny = (unsigned)ny, unz = (unsigned)nz;
+  const unsigned long long nkeys = (unsigned long long)nRings * unz * uny * unx;
+  const int keybits = (nkeys <= 1ull) ? 0 : 64 - __clzll((long long)(nkeys - 1ull));
   // ---- keys ----
   for (int e = tid; e < E; e += NT) {
     int cx = (int)floorf((S.x[e] - ox) * inv), cy = (int)floorf((S.y[e] - oy) * inv), cz = (int)floorf((S.z[e] - oz) * inv);
     cx = max(0, min(cx, nx - 1)); cy = max(0, min(cy, ny - 1)); cz = max(0, min(cz, nz - 1));
-    S.keyA[e] = ((((unsigned)S.ring[e] << bz | (unsigned)cz) << by | (unsigned)cy) << bx) | (unsigned)cx;
+    S.keyA[e] = (((unsigned)S.ring[e] * unz + (unsigned)cz) * uny + (unsigned)cy) * unx + (unsigned)cx;
     S.valA[e] = (unsigned short)e;
   }
   // ---- radix sort of (key, entry) ----
@@ -386,19 +391,30 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
     for (int p = a0 + gl; p < a1; p += G) parentS[p] = (unsigned)a0;
   }
   __syncthreads();
-  const unsigned mxm = (1u << bx) - 1u, mym = (1u << by) - 1u, mzm = (1u << bz) - 1u;
   // One 8-lane group per unit.  The 13 rows (dz,dy) that precede the unit's own cell in key order
   // and can hold linked points are located by 13 binary searches spread over the lanes; the
   // candidates of a row are then visited 8 at a time.  A candidate already in the unit's component
   // is skipped; otherwise it is tested against the unit's members until the first link.
-  for (int u = tid / G; u < nU; u += NT / G) {
+  int* unitCursor = sc + 60;
+  if (tid == 0) *unitCursor = 0;
+  __syncthreads();
+  for (;;) {
+    int u = 0;
+    if (gl == 0) u = atomicAdd(unitCursor, 1);  // units are handed out dynamically: their cost varies a lot
+    u = __shfl_sync(gmask, u, 0, G);
+    if (u >= nU) break;
     const int a0 = unitStart[u];
     const int a1 = (u + 1 < nU) ? (int)unitStart[u + 1] : E;
     const unsigned key = kS[a0];
-    const int cx = (int)(key & mxm), cy = (int)((key >> bx) & mym), cz = (int)((key >> (bx + by)) & mzm);
-    const unsigned rg = key >> (bx + by + bz);
+    const int cx = (int)(key % unx);
+    const unsigned t1 = key / unx;
+    const int cy = (int)(t1 % uny);
+    const unsigned t2 = t1 / uny;
+    const int cz = (int)(t2 % unz);
+    const unsigned rg = t2 / unz;
     int lo[2] = {0, 0}, end[2] = {0, 0};
     unsigned khi[2] = {0u, 0u};
+    unsigned mine = 0;  // bit rnd: my row of that round has candidates
 #pragma unroll
     for (int rnd = 0; rnd < 2; rnd++) {
       const int r = gl + 8 * rnd;  // 0..9: dz=-2,-1 x dy=-2..2; 10,11: dz=0, dy=-2,-1; 12: own row
@@ -407,9 +423,9 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
         const int dy = (r < 10) ? (r % 5) - 2 : (r == 12) ? 0 : r - 12;
         const int zz = cz + dz, yy = cy + dy;
         if (zz >= 0 && yy >= 0 && yy < ny) {
-          const unsigned rowk = (((rg << bz) | (unsigned)zz) << by | (unsigned)yy) << bx;
-          const unsigned klo = rowk | (unsigned)max(cx - 2, 0);
-          khi[rnd] = rowk | (unsigned)min(cx + 2, nx - 1);
+          const unsigned rowk = ((rg * unz + (unsigned)zz) * uny + (unsigned)yy) * unx;
+          const unsigned klo = rowk + (unsigned)max(cx - 2, 0);
+          khi[rnd] = rowk + (unsigned)min(cx + 2, nx - 1);
           end[rnd] = (r == 12) ? a0 : E;
           int l = 0, h = end[rnd];  // lower_bound(klo) in kS[0, end)
           while (l < h) {
@@ -417,11 +433,16 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
             if (kS[mid] < klo) l = mid + 1; else h = mid;
           }
           lo[rnd] = l;
+          if (l < end[rnd] && kS[l] <= khi[rnd]) mine |= 1u << rnd;
         }
       }
     }
-#pragma unroll 1
-    for (int r = 0; r < 13; r++) {
+    // rows that actually hold candidates: bit (8*rnd + lane)
+    unsigned rows = (__ballot_sync(gmask, mine & 1u) >> (lane & 24)) & 0xFFu;
+    rows |= ((__ballot_sync(gmask, mine & 2u) >> (lane & 24)) & 0xFFu) << 8;
+    while (rows) {
+      const int r = __ffs(rows) - 1;
+      rows &= rows - 1;
       const int src = r & 7;
       const int rlo = __shfl_sync(gmask, (r < 8) ? lo[0] : lo[1], src, G);
       const int rend = __shfl_sync(gmask, (r < 8) ? end[0] : end[1], src, G);
@@ -981,17 +1002,24 @@ __device__ __forceinline__ int surf_cell(float v, float o, float inv, int n) {
   return max(0, min(c, n - 1));
 }
 
-__global__ void __launch_bounds__(NT2, 2) k_surface_grid(
-    const float4* __restrict__ surf, const int* __restrict__ surfCnt,
-    const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
+struct SurfGlobalSm {
+  int pre[MAXCHUNK + 1];
+  int sc[40];
+  unsigned wc[(NT2 / 32) * 257];
+  unsigned rbase[256 + 32];
+};
+
+__device__ void surface_grid_scan_global(
+    SurfGlobalSm& M, const int s, const float4* __restrict__ surf, const int* __restrict__ surfCnt,
+    const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, const DevParams& P,
     unsigned* __restrict__ keyA, unsigned* __restrict__ keyB, unsigned* __restrict__ valA,
     unsigned* __restrict__ valB, float4* __restrict__ sorted, unsigned* __restrict__ sortedKey,
     int* __restrict__ rowStart, int* __restrict__ surfN, DevCounters* __restrict__ ctr) {
-  __shared__ int pre[MAXCHUNK + 1];
-  __shared__ int sc[40];
-  __shared__ unsigned wc[(NT2 / 32) * 257];
-  __shared__ unsigned rbase[256 + 32];
-  const int s = blockIdx.x, tid = threadIdx.x;
+  int* pre = M.pre;
+  int* sc = M.sc;
+  unsigned* wc = M.wc;
+  unsigned* rbase = M.rbase;
+  const int tid = threadIdx.x;
   const long long base = scan_off[s];
   const int nch = chunk_off[s + 1] - chunk_off[s];
   int* rs = rowStart + (long long)s * (P.sg_ny + 1);
@@ -1032,6 +1060,99 @@ __global__ void __launch_bounds__(NT2, 2) k_surface_grid(
     for (int rr = rp + 1; rr <= r; rr++) rs[rr] = i;
     if (i == n - 1) for (int rr = r + 1; rr <= P.sg_ny; rr++) rs[rr] = n;
   }
+}
+
+
+// Global-memory K4a.  scanList == nullptr: block b sorts scan b; otherwise the blocks loop over the
+// scans the shared-memory instantiation deferred.
+__global__ void __launch_bounds__(NT2, 2) k_surface_grid(
+    const float4* __restrict__ surf, const int* __restrict__ surfCnt,
+    const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
+    unsigned* __restrict__ keyA, unsigned* __restrict__ keyB, unsigned* __restrict__ valA,
+    unsigned* __restrict__ valB, float4* __restrict__ sorted, unsigned* __restrict__ sortedKey,
+    int* __restrict__ rowStart, int* __restrict__ surfN, DevCounters* __restrict__ ctr,
+    const int* __restrict__ scanList, const int* __restrict__ nList) {
+  __shared__ SurfGlobalSm M;
+  if (!scanList) {
+    surface_grid_scan_global(M, blockIdx.x, surf, surfCnt, scan_off, chunk_off, P, keyA, keyB, valA, valB, sorted, sortedKey,
+                             rowStart, surfN, ctr);
+  } else {
+    const int n = *nList;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+      __syncthreads();
+      surface_grid_scan_global(M, scanList[i], surf, surfCnt, scan_off, chunk_off, P, keyA, keyB, valA, valB, sorted,
+                               sortedKey, rowStart, surfN, ctr);
+    }
+  }
+}
+
+// Shared-memory K4a: the whole (key, index) sort of one scan stays in shared memory (16-bit keys
+// when the grid has <= 65536 cells), so HBM/L2 only sees the points once for the keys, once for the
+// gather, and the sorted output.  Scans with more than SCAP surface points are deferred.
+template <typename KeyT, int SCAP>
+__global__ void __launch_bounds__(NT2, 2) k_surface_grid_smem(
+    const float4* __restrict__ surf, const int* __restrict__ surfCnt,
+    const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
+    float4* __restrict__ sorted, unsigned* __restrict__ sortedKey, int* __restrict__ rowStart,
+    int* __restrict__ surfN, DevCounters* __restrict__ ctr, int* __restrict__ ovfList) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyT* kA = (KeyT*)smem_raw;
+  KeyT* kB = kA + SCAP;
+  unsigned short* vA = (unsigned short*)(kB + SCAP);
+  unsigned short* vB = vA + SCAP;
+  unsigned short* wc = vB + SCAP;                       // (NT2/32)*257
+  unsigned* rbase = (unsigned*)(wc + (NT2 / 32) * 257);  // 288; (NT2/32)*257 is even: 4-byte aligned
+  int* pre = (int*)(rbase + 288);                       // MAXCHUNK+1
+  int* sc = pre + MAXCHUNK + 1;                         // 40
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const long long base = scan_off[s];
+  const int nch = chunk_off[s + 1] - chunk_off[s];
+  int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+  if (nch > MAXCHUNK) { if (tid == 0) { atomicOr(&ctr->err, ERR_CHUNKS); surfN[s] = 0; } return; }
+  const int n = chunk_prefix<NT2>(surfCnt + chunk_off[s], nch, pre, sc);
+  if (n > SCAP) {
+    if (tid == 0) ovfList[atomicAdd(&ctr->ovf_surf, 1)] = s;
+    return;
+  }
+  if (tid == 0) surfN[s] = n;
+  if (n == 0) {
+    for (int r = tid; r <= P.sg_ny; r += NT2) rs[r] = 0;
+    return;
+  }
+  for (int i = tid; i < n; i += NT2) {
+    const float4 q = surf[piece_pos(pre, nch, i, base)];
+    const int cx = surf_cell(q.x, P.sx0, P.sg_inv, P.sg_nx), cy = surf_cell(q.y, P.sy0, P.sg_inv, P.sg_ny);
+    kA[i] = (KeyT)(((unsigned)cy << P.sg_bx) | (unsigned)cx);
+    vA[i] = (unsigned short)i;
+  }
+  const int keybits = P.sg_bx + bits_for(P.sg_ny - 1);
+  KeyT *kS = kA, *kT = kB;
+  unsigned short *vS = vA, *vT = vB;
+  for (int shift = 0; shift < keybits; shift += 8) {
+    KeyT* ki = kS; KeyT* ko = kT; unsigned short* vi = vS; unsigned short* vo = vT;
+    block_radix_pass<NT2, unsigned short>(
+        n, [=](int i) { return ((unsigned)ki[i] >> shift) & 255u; },
+        [=](int i, int pos) { ko[pos] = ki[i]; vo[pos] = vi[i]; }, wc, rbase);
+    kS = ko; kT = ki; vS = vo; vT = vi;
+  }
+  __syncthreads();
+  float4* so = sorted + base;
+  unsigned* sk = sortedKey + base;
+  for (int i = tid; i < n; i += NT2) {
+    const unsigned k = (unsigned)kS[i];
+    so[i] = surf[piece_pos(pre, nch, (int)vS[i], base)];
+    sk[i] = k;
+    const int r = (int)(k >> P.sg_bx);
+    const int rp = (i == 0) ? -1 : (int)((unsigned)kS[i - 1] >> P.sg_bx);
+    for (int rr = rp + 1; rr <= r; rr++) rs[rr] = i;
+    if (i == n - 1) for (int rr = r + 1; rr <= P.sg_ny; rr++) rs[rr] = n;
+  }
+}
+
+constexpr int SCAP16 = 12288;  // surface points per scan, 16-bit keys (2 blocks / SM)
+constexpr int SCAP32 = 8192;   // 32-bit keys
+constexpr size_t surf_smem_bytes(int scap, int keybytes) {
+  return (size_t)scap * (2 * keybytes + 4) + ((NT2 / 32) * 257) * 2 + 288 * 4 + (MAXCHUNK + 1 + 40) * 4 + 16;
 }
 
 // span of sorted positions of row r whose cell x is in [cx0, cx1]
