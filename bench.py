@@ -287,6 +287,20 @@ def main():
     if world > 1:
         dist.barrier()
     e2e_value = world * B / (e2e_ms * 1e-3)
+    # the same call with packed 12-byte xyz records (the path never reads the input intensity, src:154)
+    pin12 = PinnedBuffer((max(npts, 1), 3), np.float32)
+    pin12.array[:npts] = pts[:, :3]
+    for _ in range(2):
+        host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ko12, kp12, d12 = host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
+    torch.cuda.synchronize()
+    e2e12_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    same12 = bool(np.array_equal(ko12, ko) and np.array_equal(kp12.view(np.uint32), kp.view(np.uint32)))
+    ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)  # leave the float4 results in place for the checks below
+    pin12.free()
     h2d = npts * 16 + (B + 1) * 12 + B * 36
     d2h = int(len(kp)) * 16 + (0 if d is None else int(len(kp)) * 1980 * 4) + (B + 1) * 4 + 32
 
@@ -301,6 +315,9 @@ def main():
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "mpoints_per_s": e2e_value * npts / max(B, 1) / 1e6, "sub_batch_scans": sub_scans},
+        "e2e_packed_xyz": {"value": world * B / (e2e12_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e12_ms,
+                           "h2d_bytes_per_step": npts * 12 + (B + 1) * 12 + B * 36, "same_keypoints_as_float4": same12,
+                           "note": "fe_process_batch_layout with 12-byte xyz records"},
         "gpu_launches": launches,
         "gpu_launches_e2e": e2e_launches,
         "clocks": clocks,

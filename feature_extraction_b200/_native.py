@@ -19,7 +19,7 @@ FE_OK, FE_ERR_INVALID, FE_ERR_CUDA, FE_ERR_CAPACITY, FE_ERR_NO_DEVICE, FE_ERR_UN
 EXPORTS = [
     "fe_params_node_default", "fe_params_launch_playback", "fe_version", "fe_create", "fe_set_params",
     "fe_destroy", "fe_last_error", "fe_device_count", "fe_host_alloc", "fe_host_free",
-    "fe_process_batch", "fe_process_batch_device", "fe_download", "fe_enable_cloud_outputs", "fe_get_cloud_outputs",
+    "fe_process_batch", "fe_process_batch_layout", "fe_imu_to_roll_pitch", "fe_process_batch_device", "fe_download", "fe_enable_cloud_outputs", "fe_get_cloud_outputs",
     "fe_get_stage_times", "fe_timer_begin", "fe_timer_end", "fe_get_batch_stats", "fe_get_elevation_angles", "fe_rotate_cloud", "fe_rotation_matrix",
     "fe_filter_cloud", "fe_extract_clusters", "fe_get_cylinder_segments", "fe_estimate_keypoints",
     "fe_estimate_descriptors", "fe_pack_point_descriptors",
@@ -51,6 +51,11 @@ class Limits(C.Structure):
         ("max_keypoints_per_call", C.c_int64),
         ("max_ring_clusters_per_call", C.c_int64),
     ]
+
+
+class PointLayout(C.Structure):
+    """fe_point_layout_t: PointCloud2-style record layout (stride = point_step)."""
+    _fields_ = [("stride", C.c_int32), ("x_off", C.c_int32), ("y_off", C.c_int32), ("z_off", C.c_int32)]
 
 
 class BatchResult(C.Structure):
@@ -91,6 +96,9 @@ def lib():
         L.fe_destroy.argtypes = [C.c_void_p]
         L.fe_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.fe_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(BatchResult)]
+        L.fe_process_batch_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PointLayout), C.c_void_p, C.c_void_p, C.c_int32,
+                                              C.POINTER(BatchResult)]
+        L.fe_imu_to_roll_pitch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.fe_process_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(BatchResult)]
         L.fe_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.fe_enable_cloud_outputs.argtypes = [C.c_void_p, C.c_int32]

@@ -399,14 +399,14 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
 // Enqueue the kernels of one sub-batch whose points are at d_pts.  k1flags selects what K1 does;
 // `fromStage`: 0 = K1 first; 1 = crop/cropMeta/cropCnt already filled by the caller.
 int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int64_t npts, int nch,
-                     int k1flags, bool doDesc, bool singleRing, bool wantKc) {
+                     int k1flags, bool doDesc, bool singleRing, bool wantKc, RawLayout lay = RawLayout{nullptr, 0, 0, 0, 0}) {
   DevParams& P = ctx->dp;
   s.nev = 0;
   mark(ctx, s, "begin");
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), s.stream));
   if (nch > 0 && k1flags >= 0) {
     k_level_crop_ring<<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
-                                                 s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr);
+                                                 s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
     ctx->launches++;
   }
   mark(ctx, s, "K1 level+crop+ring");
@@ -662,8 +662,8 @@ int fe_get_stage_times(fe_ctx_t* ctx, int32_t cap, const char** names, float* ms
 
 // ---- the fused path ------------------------------------------------------------------------------
 
-int fe_process_batch(fe_ctx_t* ctx, const fe_point_t* points, const int64_t* scan_offsets,
-                     const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out) {
+static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int stride, int xo, int yo, int zo, bool isFloat4,
+                              const int64_t* scan_offsets, const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out) {
   if (!ctx || !out || n_scans < 0 || (n_scans > 0 && (!scan_offsets || !roll_pitch))) return FE_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   ctx->err.clear();
@@ -687,8 +687,8 @@ int fe_process_batch(fe_ctx_t* ctx, const fe_point_t* points, const int64_t* sca
     while (last < n_scans && (last - first) < s.capScans) {
       const int64_t n = scan_offsets[last + 1] - scan_offsets[last];
       if (n < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must be non-decreasing");
-      if (n > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "a single scan exceeds max_points_per_call");
-      if (npts + n > s.capPts) break;
+      if (n > s.capPts || n * stride > s.capPts * 16) return fail(ctx, FE_ERR_CAPACITY, "a single scan exceeds max_points_per_call");
+      if (npts + n > s.capPts || (npts + n) * stride > s.capPts * 16) break;
       npts += n;
       last++;
     }
@@ -697,10 +697,11 @@ int fe_process_batch(fe_ctx_t* ctx, const fe_point_t* points, const int64_t* sca
     st = stage_scans(ctx, s, scan_offsets + first, roll_pitch + 2 * first, ns, &np2, &nch);
     if (st) return st;
     if (npts > 0)
-      CK(cudaMemcpyAsync(s.d_pts, points + scan_offsets[first], (size_t)npts * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
+      CK(cudaMemcpyAsync(s.d_pts, points + scan_offsets[first] * (int64_t)stride, (size_t)npts * (size_t)stride, cudaMemcpyHostToDevice, s.stream));
     const bool wantKc = ctx->cloudOutputs;
     if (wantKc) { st = ensure_kc(ctx, s); if (st) return st; }
-    st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, wantKc);
+    RawLayout lay = {isFloat4 ? nullptr : (const unsigned char*)s.d_pts, stride, xo, yo, zo};
+    st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, wantKc, lay);
     if (st) return st;
     s.busy = true; s.nscans = ns; s.npts = npts; s.firstScan = first;
     nsub++;
@@ -734,6 +735,51 @@ int fe_process_batch(fe_ctx_t* ctx, const fe_point_t* points, const int64_t* sca
   out->descriptors = desc ? ctx->h_desc : nullptr;
   out->on_device = 0;
   out->gpu_launches = ctx->launches - launches0;
+  return FE_OK;
+}
+
+int fe_process_batch(fe_ctx_t* ctx, const fe_point_t* points, const int64_t* scan_offsets,
+                     const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out) {
+  return process_batch_host(ctx, (const unsigned char*)points, 16, 0, 4, 8, true, scan_offsets, roll_pitch, n_scans, out);
+}
+
+int fe_process_batch_layout(fe_ctx_t* ctx, const void* points, const fe_point_layout_t* layout,
+                            const int64_t* scan_offsets, const double* roll_pitch, int32_t n_scans,
+                            fe_batch_result_t* out) {
+  if (!ctx || !layout) return FE_ERR_INVALID;
+  const fe_point_layout_t& L = *layout;
+  if (L.stride < 12 || L.stride > 4096 || L.x_off < 0 || L.y_off < 0 || L.z_off < 0 || L.x_off + 4 > L.stride ||
+      L.y_off + 4 > L.stride || L.z_off + 4 > L.stride)
+    return fail(ctx, FE_ERR_INVALID, "fe_point_layout: need 12 <= stride <= 4096 and x/y/z floats inside the record");
+  return process_batch_host(ctx, (const unsigned char*)points, L.stride, L.x_off, L.y_off, L.z_off, false, scan_offsets,
+                            roll_pitch, n_scans, out);
+}
+
+// tf::Matrix3x3(quat).getRPY(tmproll, pitch, yaw) as imuCallback uses it (src:60-65)
+int fe_imu_to_roll_pitch(const double q[4], int32_t cloud_leveling, double* roll, double* pitch) {
+  if (!q || !roll || !pitch) return FE_ERR_INVALID;
+  if (!cloud_leveling) { *roll = 0.0; *pitch = 0.0; return FE_OK; }  // src:66-69
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  // Matrix3x3::setRotation
+  const double d = x * x + y * y + z * z + w * w;
+  const double s = 2.0 / d;
+  const double xs = x * s, ys = y * s;
+  const double wx = w * xs, wy = w * ys;
+  const double xx = x * xs, xz = x * (z * s);
+  const double yy = y * ys, yz = y * (z * s);
+  const double m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+  // Matrix3x3::getEulerYPR, solution 1
+  double tmproll, p;
+  if (fabs(m20) >= 1.0) {
+    const double delta = atan2(m21, m22);
+    p = (m20 < 0.0) ? 3.14159265358979323846 / 2.0 : -3.14159265358979323846 / 2.0;
+    tmproll = delta;
+  } else {
+    p = -asin(m20);
+    tmproll = atan2(m21 / cos(p), m22 / cos(p));
+  }
+  *roll = tmproll - 3.14159265358979323846;  // src:65
+  *pitch = p;
   return FE_OK;
 }
 
@@ -842,7 +888,7 @@ static int stage_k1(fe_ctx* ctx, fe_point_t* cloud, int64_t n, double roll, doub
   if (st) return st;
   CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   k_level_crop_ring<<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
-                                               s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full);
+                                               s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full, RawLayout{nullptr, 0, 0, 0, 0});
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(cloud, s.d_full, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
@@ -877,7 +923,7 @@ static int stage_upload_k1(fe_ctx* ctx, Slot& s, const fe_point_t* in, int64_t n
   if (n > 0) CK(cudaMemcpyAsync(s.d_pts, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   if (*nchOut > 0) {
     k_level_crop_ring<<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
-                                                     s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr);
+                                                     s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, RawLayout{nullptr, 0, 0, 0, 0});
     ctx->launches++;
   }
   CK(cudaGetLastError());

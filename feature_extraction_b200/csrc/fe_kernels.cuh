@@ -119,6 +119,21 @@ __device__ __forceinline__ float elevation_deg(float xf, float yf, float zf) {
   return elevation_deg_literal(xf, yf, zf);
 }
 
+// 32-bit float at any byte address (PointCloud2 records with point_step 22 are only 2-byte aligned)
+__device__ __forceinline__ float load_f32_any(const unsigned char* p) {
+  const unsigned long long a = (unsigned long long)p;
+  unsigned v;
+  if ((a & 3ull) == 0ull) v = __ldg((const unsigned*)p);
+  else if ((a & 1ull) == 0ull) v = (unsigned)__ldg((const unsigned short*)p) | ((unsigned)__ldg((const unsigned short*)(p + 2)) << 16);
+  else v = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16) | ((unsigned)__ldg(p + 3) << 24);
+  return __uint_as_float(v);
+}
+
+struct RawLayout {  // records of fe_point_layout_t; raw == nullptr: the input is float4
+  const unsigned char* raw;
+  int stride, xo, yo, zo;
+};
+
 // ============================================================================================
 // K1 — fused elevation / level / crop / ring-bucket, order-preserving compaction per chunk.
 // Block = one chunk of CH consecutive points of one scan; 256 threads; warp w owns points
@@ -130,7 +145,8 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
     const float4* __restrict__ pts, const long long* __restrict__ scan_off,
     const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
     int flags, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
-    unsigned* __restrict__ cropMeta, int* __restrict__ cropCnt, float4* __restrict__ full_out) {
+    unsigned* __restrict__ cropMeta, int* __restrict__ cropCnt, float4* __restrict__ full_out,
+    RawLayout L) {
   __shared__ int s_scan;
   __shared__ int s_ws[8], s_wc[8];
   const int chunk = blockIdx.x;
@@ -162,7 +178,13 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
     bool fs = false, fc = false;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (j < nIn) {
-      const float4 p = __ldg(pts + base + j);
+      float4 p;
+      if (L.raw) {  // PointCloud2-style records decoded in place
+        const unsigned char* rec = L.raw + (base + j) * (long long)L.stride;
+        p = make_float4(load_f32_any(rec + L.xo), load_f32_any(rec + L.yo), load_f32_any(rec + L.zo), 0.0f);
+      } else {
+        p = __ldg(pts + base + j);
+      }
       float el = p.w;
       if (flags & F_ELEV) el = elevation_deg(p.x, p.y, p.z);  // getElevationAngles, src:147-156
       if (flags & F_ROT) {

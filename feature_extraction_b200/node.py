@@ -190,6 +190,21 @@ class FeatureExtractionNode:
         return {"keypoints": kp, "descriptors": d}
 
     # -- batched form --------------------------------------------------------------------------
+    def imuCallback(self, quat_xyzw, cloud_leveling=True):
+        """src:57-70: orientation quaternion -> this node's roll/pitch state."""
+        self.roll, self.pitch = imu_to_roll_pitch(quat_xyzw, cloud_leveling)
+
+    def processBatchLayout(self, raw, stride, x_off, y_off, z_off, scan_offsets, roll_pitch, copy=True):
+        """fe_process_batch_layout: `raw` is a contiguous uint8/any-dtype host buffer of records."""
+        buf = np.ascontiguousarray(raw)
+        lay = N.PointLayout(int(stride), int(x_off), int(y_off), int(z_off))
+        offs = np.ascontiguousarray(scan_offsets, np.int64)
+        rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
+        B = len(offs) - 1
+        res = N.BatchResult()
+        self._check(N.lib().fe_process_batch_layout(self._ctx, _ptr(buf), C.byref(lay), _ptr(offs), _ptr(rp), B, C.byref(res)))
+        return self._unpack(res, B, copy)
+
     def processBatch(self, points, scan_offsets, roll_pitch, copy=True):
         """fe_process_batch: HOST buffers in, host results out (CSR by scan).
 
@@ -202,6 +217,9 @@ class FeatureExtractionNode:
         B = len(offs) - 1
         res = N.BatchResult()
         self._check(N.lib().fe_process_batch(self._ctx, _ptr(c), _ptr(offs), _ptr(rp), B, C.byref(res)))
+        return self._unpack(res, B, copy)
+
+    def _unpack(self, res, B, copy):
         self.last_launches = int(res.gpu_launches)
         K = int(res.n_keypoints)
         ko = np.ctypeslib.as_array(res.keypoint_offsets, shape=(B + 1,))
@@ -276,6 +294,16 @@ class FeatureExtractionNode:
         n = C.c_int32(0)
         self._check(N.lib().fe_get_stage_times(self._ctx, 32, names, ms, C.byref(n)))
         return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+
+def imu_to_roll_pitch(quat_xyzw, cloud_leveling=True):
+    """imuCallback (src:57-70): quaternion {x,y,z,w} -> (roll, pitch) as the node stores them."""
+    q = np.ascontiguousarray(quat_xyzw, np.float64)
+    r, p = C.c_double(0), C.c_double(0)
+    st = N.lib().fe_imu_to_roll_pitch(_ptr(q), 1 if cloud_leveling else 0, C.byref(r), C.byref(p))
+    if st != N.FE_OK:
+        raise FeatureExtractionError(st, "fe_imu_to_roll_pitch")
+    return float(r.value), float(p.value)
 
 
 def rotation_matrix(roll, pitch):

@@ -108,6 +108,25 @@ typedef struct fe_batch_result {
 int fe_process_batch(fe_ctx_t* ctx, const fe_point_t* points, const int64_t* scan_offsets,
                      const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out);
 
+/* Layout of the caller's point records (sensor_msgs/PointCloud2 point_step and field offsets, or any
+ * array of structs): x, y, z are little-endian 32-bit floats at byte offsets x_off, y_off, z_off of
+ * records `stride` bytes apart.  The input intensity is never read: getElevationAngles overwrites it
+ * (src:154).  Examples: {16,0,4,8} fe_point_t; {12,0,4,8} packed xyz; {32,0,4,8} pcl::PointXYZI as
+ * it sits in a pcl::PointCloud; {22,0,4,8} / {32,0,4,8} Velodyne PointCloud2 data (src:79-81). */
+typedef struct fe_point_layout {
+  int32_t stride, x_off, y_off, z_off;
+} fe_point_layout_t;
+
+/* fe_process_batch for records of any layout: `points` is the HOST byte buffer, scan_offsets count
+ * records.  The records are copied to the device as they are and decoded by the first kernel. */
+int fe_process_batch_layout(fe_ctx_t* ctx, const void* points, const fe_point_layout_t* layout,
+                            const int64_t* scan_offsets, const double* roll_pitch, int32_t n_scans,
+                            fe_batch_result_t* out);
+
+/* imuCallback, src:57-70: orientation quaternion {x,y,z,w} -> the roll/pitch the node keeps
+ * (tf::Matrix3x3(quat).getRPY, roll = tmproll - pi; both 0 when cloud_leveling is false). */
+int fe_imu_to_roll_pitch(const double quat_xyzw[4], int32_t cloud_leveling, double* roll, double* pitch);
+
 /* Same, but `d_points` is already resident in device memory and the results stay on the
  * device (keypoint_offsets is still host memory).  Must fit one sub-batch. */
 int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points,

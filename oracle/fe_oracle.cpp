@@ -723,6 +723,37 @@ void feo_std_sort_cluster_order(const int32_t* sizes, int32_t n, int32_t* order_
   for (int i = 0; i < n; i++) order_out[i] = v[i].id;
 }
 
+// imuCallback, src:57-70: tf::quaternionMsgToTF + tf::Matrix3x3(quat).getRPY(tmproll, pitch, yaw)
+// [tf/LinearMath/Matrix3x3.h, not vendored: setRotation + getEulerYPR solution 1, tfScalar = double].
+int feo_imu_to_roll_pitch(const double q[4], int32_t levelCloud, double* roll_out, double* pitch_out) {
+  double roll, pitch;
+  if (levelCloud) {
+    const double qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+    double d = qx * qx + qy * qy + qz * qz + qw * qw;  // Quaternion::length2
+    double s = 2.0 / d;
+    double xs = qx * s, ys = qy * s, zs = qz * s;
+    double wx = qw * xs, wy = qw * ys;
+    double xx = qx * xs, xz = qx * zs;
+    double yy = qy * ys, yz = qy * zs;
+    double m_el2_x = xz - wy, m_el2_y = yz + wx, m_el2_z = 1.0 - (xx + yy);
+    double tmproll;
+    if (fabs(m_el2_x) >= 1) {  // gimbal lock
+      double delta = atan2(m_el2_y, m_el2_z);
+      if (m_el2_x < 0) { pitch = M_PI / 2.0; tmproll = delta; }
+      else { pitch = -M_PI / 2.0; tmproll = delta; }
+    } else {
+      pitch = -asin(m_el2_x);
+      tmproll = atan2(m_el2_y / cos(pitch), m_el2_z / cos(pitch));
+    }
+    roll = tmproll - M_PI;  // src:65
+  } else {
+    roll = 0.0;   // src:67-68
+    pitch = 0.0;
+  }
+  *roll_out = roll; *pitch_out = pitch;
+  return FE_OK;
+}
+
 // One scan through the whole path (cloudCallback, src:83-117).  Any output pointer may be NULL.
 int feo_process_scan(const fe_params_t* P, const fe_point_t* points, int64_t n, double roll,
                      double pitch, int32_t mode,

@@ -189,6 +189,13 @@ def std_sort_cluster_order(sizes):
     return out
 
 
+def imu_to_roll_pitch(quat_xyzw, cloud_leveling=True):
+    q = np.ascontiguousarray(quat_xyzw, np.float64)
+    r, p = C.c_double(0), C.c_double(0)
+    lib().feo_imu_to_roll_pitch(_p(q), C.c_int32(1 if cloud_leveling else 0), C.byref(r), C.byref(p))
+    return float(r.value), float(p.value)
+
+
 def process_scan(params, points, roll, pitch, mode=0, want_clouds=False):
     """cloudCallback (src:83-117) for one scan.  -> dict"""
     c = _pts(points)

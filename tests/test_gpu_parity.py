@@ -143,3 +143,20 @@ def test_cpp_host_mirror_example_runs():
     out = subprocess.run([os.path.join(root, "examples", "core_example")], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "identical" in out.stdout and "1 keypoints" in out.stdout
+
+
+@pytest.mark.parametrize("stride,offs", [(12, (0, 4, 8)), (16, (0, 4, 8)), (32, (0, 4, 8)), (22, (0, 4, 8)), (32, (4, 12, 20)), (19, (1, 6, 11))])
+def test_record_layouts_decode_on_device(ob, synth, nodes, stride, offs):
+    """PointCloud2-style records (point_step / field offsets, incl. the 2-byte aligned
+    22-byte Velodyne layout and a deliberately odd one) give the same result as fe_point_t input."""
+    nd = nodes(2)
+    pts, so, rp = synth.generate(2, 5, scan_index_base=900)
+    ko, kp, d = nd.processBatch(pts, so, rp)
+    raw = np.zeros((len(pts), stride), np.uint8)
+    raw[:] = 0xAB  # junk in the unused bytes
+    for k, o in enumerate(offs):
+        raw[:, o:o + 4] = pts[:, k].copy().view(np.uint8).reshape(-1, 4)
+    ko2, kp2, d2 = nd.processBatchLayout(raw, stride, offs[0], offs[1], offs[2], so, rp)
+    assert np.array_equal(ko, ko2) and bits_equal(kp, kp2)
+    from util import rel_err
+    assert rel_err(d2, d).max() < 1e-5

@@ -114,3 +114,23 @@ def test_cpp_host_mirror_builds_against_the_c_abi():
     import subprocess
     subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "examples")])
     assert os.path.exists(os.path.join(ROOT, "examples", "core_example"))
+
+
+def test_imu_to_roll_pitch_matches_oracle_and_known_cases(ob):
+    """imuCallback (src:57-70): tf getRPY, roll = tmproll - pi; zeros when cloud_leveling is false."""
+    from feature_extraction_b200 import imu_to_roll_pitch
+    r, p = imu_to_roll_pitch([0, 0, 0, 1])
+    assert r == -np.pi and p == 0.0
+    # a sensor mounted upside down (roll = pi) is what the "- pi" is there for
+    r, p = imu_to_roll_pitch([1, 0, 0, 0])
+    assert abs(r) < 1e-12 and abs(p) < 1e-12
+    assert imu_to_roll_pitch([0.3, 0.1, -0.2, 0.9], cloud_leveling=False) == (0.0, 0.0)
+    rng = np.random.default_rng(9)
+    for _ in range(500):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        assert imu_to_roll_pitch(q) == ob.imu_to_roll_pitch(q)
+    # pitch = 30 deg about y, then check against the closed form
+    a = np.deg2rad(30.0)
+    r, p = imu_to_roll_pitch([0, np.sin(a / 2), 0, np.cos(a / 2)])
+    assert abs(p - a) < 1e-12 and abs(r + np.pi) < 1e-12
