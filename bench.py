@@ -162,7 +162,8 @@ def stage_bytes(st, desc_len=1980):
     N, Ns, Nc, Kf, K, M = (st[k] for k in ("points", "surface_points", "crop_points", "ring_clusters", "keypoints", "neighbours"))
     return {
         "K1 level+crop+ring": 16 * N + 16 * Ns + 20 * Nc,
-        "K2+K3 ring clusters + merge": 20 * Nc + 32 * Kf + 16 * K,
+        "K2 ring clusters": 20 * Nc + 16 * Kf,
+        "K3 merge keypoints": 16 * Kf + 16 * K,
         "keypoint CSR": 32 * K,
         "K4a surface grid": 16 * Ns + 20 * Ns,
         "K4b mark neighbours": 16 * M + 4 * M,

@@ -347,11 +347,27 @@ int set_kernel_attrs(fe_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_desc_hist<256, DCAP, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)desc_smem_bytes(DCAP, 256)));
+  CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_M, DCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)desc_smem_bytes(DCAP_M, 512)));
+  CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_L, DCAP_M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)desc_smem_bytes(DCAP_L, 512)));
   CK(cudaFuncSetAttribute(k_surface_grid_smem<unsigned short, SCAP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)surf_smem_bytes(SCAP16, 2)));
   CK(cudaFuncSetAttribute(k_surface_grid_smem<unsigned, SCAP32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)surf_smem_bytes(SCAP32, 4)));
   return FE_OK;
+}
+
+// K4d: three instantiations split the keypoints by neighbour count (smaller footprint = more blocks / SM)
+void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp) {
+#define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P, \
+                     s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_desc, s.d_ctr
+  k_desc_hist<256, DCAP, 0, false><<<gridKp, 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<512, DCAP_M, DCAP, false><<<std::min(gridKp, 148 * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<512, DCAP_L, DCAP_M, true><<<std::min(gridKp, 148), 512, desc_smem_bytes(DCAP_L, 512), s.stream>>>(FE_DESC_ARGS);
+#undef FE_DESC_ARGS
+  ctx->launches += 3;
 }
 
 // K4a: shared-memory sort for scans that fit, global-memory sort for the deferred rest.
@@ -371,7 +387,9 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
 
 // K2 + K3 for `nscans` scans: the 2-blocks-per-SM instantiation first, then the large one over
 // whatever scans it deferred (an immediate exit when there are none).
-void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool wantKc, bool merge) {
+void mark(fe_ctx* ctx, Slot& s, const char* name);
+
+void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool wantKc, bool merge, bool marks = false) {
   const DevParams& P = ctx->dp;
   const int gridL = std::min(nscans, 148);
   int* ovfR = &s.d_ctr->ovf_rings;
@@ -386,6 +404,7 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
                                                                       singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
                                                                       s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr);
   ctx->launches += 2;
+  if (marks) mark(ctx, s, "K2 ring clusters");
   if (merge) {
     k_merge_keypoints<ECAP_M, NTM, 8><<<nscans, NTM, kClusterSmemM, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool,
                                                                                 (int)s.capKp, s.d_kpBase, s.d_kpCnt, s.d_ctr, nullptr,
@@ -405,13 +424,17 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
   mark(ctx, s, "begin");
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), s.stream));
   if (nch > 0 && k1flags >= 0) {
-    k_level_crop_ring<<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
-                                                 s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
+    if (lay.raw)
+      k_level_crop_ring<true><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+                                                         s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
+    else
+      k_level_crop_ring<false><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+                                                          s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
     ctx->launches++;
   }
   mark(ctx, s, "K1 level+crop+ring");
-  launch_clustering(ctx, s, nscans, singleRing, wantKc, true);
-  mark(ctx, s, "K2+K3 ring clusters + merge");
+  launch_clustering(ctx, s, nscans, singleRing, wantKc, true, true);
+  mark(ctx, s, "K3 merge keypoints");
   k_kp_offsets<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr);
   ctx->launches++;
   k_kp_gather<<<std::max(1, std::min(1024, (nscans * 8 + 255) / 256)), 256, 0, s.stream>>>(s.d_kpPool, s.d_kpBase, s.d_kpOff, nscans,
@@ -435,10 +458,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
       ctx->launches++;
     }
     mark(ctx, s, "K4c density");
-    k_desc_hist<<<gridKp, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, s.d_sortedKey,
-                                              s.d_rowStart, s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap,
-                                              s.d_desc, s.d_ctr);
-    ctx->launches++;
+    launch_desc_hist(ctx, s, nscans, P, gridKp);
     mark(ctx, s, "K4d shape context");
   }
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
@@ -835,12 +855,12 @@ int fe_timer_end(fe_ctx_t* ctx, float* elapsed_ms) {
   return FE_OK;
 }
 
-int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[8]) {
+int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[10]) {
   if (!ctx || !out || !ctx->slot[0].stream) return FE_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   Slot& s = ctx->slot[0];
   CK(cudaStreamSynchronize(s.stream));
-  for (int i = 0; i < 8; i++) out[i] = 0;
+  for (int i = 0; i < 10; i++) out[i] = 0;
   out[0] = s.npts;
   std::vector<int> a((size_t)std::max(s.lastNch, 1)), b((size_t)std::max(s.lastNch, 1));
   if (s.lastNch > 0) {
@@ -862,6 +882,8 @@ int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[8]) {
   }
   out[6] = s.h_ctr->ovf_rings;
   out[7] = s.h_ctr->ovf_merge;
+  out[8] = s.h_ctr->ovf_surf;
+  out[9] = s.h_ctr->desc_unordered;
   return FE_OK;
 }
 
@@ -887,7 +909,7 @@ static int stage_k1(fe_ctx* ctx, fe_point_t* cloud, int64_t n, double roll, doub
   st = stage_scans(ctx, s, offs, rp, 1, &npts, &nch);
   if (st) return st;
   CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
-  k_level_crop_ring<<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+  k_level_crop_ring<false><<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
                                                s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full, RawLayout{nullptr, 0, 0, 0, 0});
   ctx->launches++;
   CK(cudaGetLastError());
@@ -922,7 +944,7 @@ static int stage_upload_k1(fe_ctx* ctx, Slot& s, const fe_point_t* in, int64_t n
   if (st) return st;
   if (n > 0) CK(cudaMemcpyAsync(s.d_pts, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   if (*nchOut > 0) {
-    k_level_crop_ring<<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+    k_level_crop_ring<false><<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
                                                      s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, RawLayout{nullptr, 0, 0, 0, 0});
     ctx->launches++;
   }
@@ -1095,9 +1117,7 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
                                                                                (long long)n, s.d_rho);
     ctx->launches++;
   }
-  k_desc_hist<<<148 * 4, 256, 0, q>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, 1, s.d_kpNbr, s.d_sorted, s.d_sortedKey, s.d_rowStart,
-                                      s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_desc, s.d_ctr);
-  ctx->launches += 2;
+  launch_desc_hist(ctx, s, 1, P, 148 * 4);
   ctx->dp = saved;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, q));

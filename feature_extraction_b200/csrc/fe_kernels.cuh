@@ -74,6 +74,8 @@ struct DevCounters {
   int ovf_rings;   // scans deferred from K2 to its large instantiation
   int ovf_merge;   // scans deferred from K3 to its large instantiation
   int ovf_surf;    // scans deferred from the shared-memory K4a to the global-memory one
+  int desc_unordered;  // keypoints with more than DCAP contributions (summed with atomics, not in PCL's order)
+  int pad[3];
 };
 
 // getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
@@ -141,6 +143,7 @@ struct RawLayout {  // records of fe_point_layout_t; raw == nullptr: the input i
 // the chunk's own slot of the output arrays (same CSR as the input) with their counts, so the
 // per-scan consumers concatenate pieces in order and no global prefix sum is needed.
 // ============================================================================================
+template <bool RAW>
 __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
     const float4* __restrict__ pts, const long long* __restrict__ scan_off,
     const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (j < nIn) {
       float4 p;
-      if (L.raw) {  // PointCloud2-style records decoded in place
+      if (RAW) {  // PointCloud2-style records decoded in place
         const unsigned char* rec = L.raw + (base + j) * (long long)L.stride;
         p = make_float4(load_f32_any(rec + L.xo), load_f32_any(rec + L.yo), load_f32_any(rec + L.zo), 0.0f);
       } else {
@@ -251,7 +254,11 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
   const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    if (fl & (1u << r)) surf[base + os + __popc(ms[r] & lt)] = o[r];
+    if (fl & (1u << r)) {
+      float4 sq = o[r];  // 3DSC reads only x,y,z of the surface: .w carries the point's index in the scan
+      sq.w = __int_as_float(c * CH + w * 256 + r * 32 + lane);
+      surf[base + os + __popc(ms[r] & lt)] = sq;
+    }
     if (fl & (1u << (8 + r))) {
       const long long d = base + oc + __popc(mc[r] & lt);
       crop[d] = o[r];
@@ -407,10 +414,11 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
   constexpr int G = 8;
   const int gl = lane & (G - 1);
   const unsigned gmask = 0xFFu << (lane & 24);
+  unsigned short* unitOf = S.aux;  // unit index of every sorted position
   for (int u = tid / G; u < nU; u += NT / G) {
     const int a0 = unitStart[u];
     const int a1 = (u + 1 < nU) ? (int)unitStart[u + 1] : E;
-    for (int p = a0 + gl; p < a1; p += G) parentS[p] = (unsigned)a0;
+    for (int p = a0 + gl; p < a1; p += G) { parentS[p] = (unsigned)a0; unitOf[p] = (unsigned short)u; }
   }
   __syncthreads();
   // One 8-lane group per unit.  The 13 rows (dz,dy) that precede the unit's own cell in key order
@@ -469,21 +477,57 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
       const int rlo = __shfl_sync(gmask, (r < 8) ? lo[0] : lo[1], src, G);
       const int rend = __shfl_sync(gmask, (r < 8) ? end[0] : end[1], src, G);
       const unsigned rkhi = __shfl_sync(gmask, (r < 8) ? khi[0] : khi[1], src, G);
-      for (int q0 = rlo; q0 < rend; q0 += G) {
-        const int q = q0 + gl;
-        const bool in = (q < rend) && (kS[q] <= rkhi);
-        if (in && uf_find(parentS, (unsigned)q) != uf_find(parentS, (unsigned)a0)) {
-          const unsigned e2 = vS[q];
-          const float qx = S.x[e2], qy = S.y[e2], qz = S.z[e2];
-          for (int a = a0; a < a1; a++) {
-            const unsigned ea = vS[a];
-            if (l2_simple(S.x[ea], S.y[ea], S.z[ea], qx, qy, qz) < r2f) {
-              uf_union(parentS, (unsigned)a0, (unsigned)q);
-              break;
+      // Candidate units (cells) of this row — at most five, one lane each.  All points of a unit are
+      // in one component, so one root comparison decides whether the unit matters.  Small unit pairs
+      // are tested by the lane that owns them; large ones (dense cells) are flagged and then tested
+      // by the whole group, the pair tests spread over the 8 lanes, stopping at the first link.
+      for (int uu0 = unitOf[rlo];; uu0 += G) {
+        const int uu = uu0 + gl;
+        bool in = false, heavy = false;
+        if (uu < nU) {
+          const int b0 = unitStart[uu];
+          in = (b0 < rend) && (kS[b0] <= rkhi);
+          if (in && uf_find(parentS, (unsigned)b0) != uf_find(parentS, (unsigned)a0)) {
+            const int b1 = (uu + 1 < nU) ? (int)unitStart[uu + 1] : E;
+            if ((a1 - a0) * (b1 - b0) <= 96) {
+              bool linked = false;
+              for (int a = a0; a < a1 && !linked; a++) {
+                const unsigned ea = vS[a];
+                const float ax = S.x[ea], ay = S.y[ea], az = S.z[ea];
+                for (int b = b0; b < b1; b++) {
+                  const unsigned eb = vS[b];
+                  if (l2_simple(ax, ay, az, S.x[eb], S.y[eb], S.z[eb]) < r2f) { linked = true; break; }
+                }
+              }
+              if (linked) uf_union(parentS, (unsigned)a0, (unsigned)b0);
+            } else {
+              heavy = true;
             }
           }
         }
-        if (!__shfl_sync(gmask, (int)in, G - 1, G)) break;  // keys are sorted: nothing further in range
+        unsigned hv = (__ballot_sync(gmask, heavy) >> (lane & 24)) & 0xFFu;
+        while (hv) {
+          const int ub = uu0 + __ffs(hv) - 1;
+          hv &= hv - 1;
+          const int b0 = unitStart[ub];
+          const int b1 = (ub + 1 < nU) ? (int)unitStart[ub + 1] : E;
+          int differs = 0;  // re-checked (unions happened meanwhile); by lane 0 so that it is uniform
+          if (gl == 0) differs = (uf_find(parentS, (unsigned)b0) != uf_find(parentS, (unsigned)a0)) ? 1 : 0;
+          differs = __shfl_sync(gmask, differs, 0, G);
+          if (!differs) continue;
+          bool linked = false;
+          for (int a = a0; a < a1; a++) {
+            const unsigned ea = vS[a];
+            const float ax = S.x[ea], ay = S.y[ea], az = S.z[ea];
+            for (int b = b0 + gl; b < b1; b += G) {
+              const unsigned eb = vS[b];
+              if (l2_simple(ax, ay, az, S.x[eb], S.y[eb], S.z[eb]) < r2f) { linked = true; break; }
+            }
+            if (__ballot_sync(gmask, linked) != 0u) { linked = true; break; }
+          }
+          if (linked && gl == 0) uf_union(parentS, (unsigned)a0, (unsigned)b0);
+        }
+        if (!__shfl_sync(gmask, (int)in, G - 1, G)) break;  // units are in key order: nothing further in range
       }
     }
   }
@@ -1280,32 +1324,116 @@ __device__ __forceinline__ float eigen_sum3(float a0, float a1, float a2) {
   return __fadd_rn(a0, __fadd_rn(a1, a2));  // Eigen's unrolled 3-term reduction: a0 + (a1 + a2)
 }
 
-__global__ void __launch_bounds__(256) k_desc_hist(
+constexpr int DCAP = 1536;    // contributions per keypoint of the fast instantiation (256 threads, 5 blocks / SM)
+constexpr int DCAP_M = 4096;  // of the medium instantiation (512 threads, 2 blocks / SM)
+constexpr int DCAP_L = 8192;  // of the large instantiation (512 threads, 1 block / SM)
+constexpr size_t desc_smem_bytes(int cap, int nt) {
+  return (size_t)cap * 24 + FE_DESC_LEN * 4 + 64 + 0 * nt;
+}
+
+// One neighbour's contribution (3dsc.hpp computePoint, the body of the neighbour loop): bin and
+// weight.  Returns false when PCL skips the neighbour.  o = keypoint, q = surface point,
+// (axx, axy, -0) = normalised x axis, dens = local point density of q.
+__device__ __forceinline__ bool shape_context_contribution(const float4 o, const float4 q, const float d2, const float axx,
+                                                           const float axy, const DevParams& P, const float* __restrict__ lut,
+                                                           const int dens, int& bin, float& wgt) {
+  if (fabsf(d2 - 0.0f) < 1.17549435e-38f) return false;  // pcl::utils::equal(nn_dists, 0)
+  if (dens <= 0) return false;
+  const float axz = -0.0f;
+  const float rr = __fsqrt_rn(d2);
+  // pcl::geometry::project(neighbour, origin, normal=(0,0,1), proj); proj -= origin
+  const float pox = __fsub_rn(q.x, o.x), poy = __fsub_rn(q.y, o.y), poz = __fsub_rn(q.z, o.z);
+  const float lambda = eigen_sum3(__fmul_rn(0.0f, pox), __fmul_rn(0.0f, poy), __fmul_rn(1.0f, poz));
+  float prx = __fsub_rn(__fsub_rn(q.x, __fmul_rn(lambda, 0.0f)), o.x);
+  float pry = __fsub_rn(__fsub_rn(q.y, __fmul_rn(lambda, 0.0f)), o.y);
+  float prz = __fsub_rn(__fsub_rn(q.z, __fmul_rn(lambda, 1.0f)), o.z);
+  {  // Eigen 3.2 normalize(): multiply by 1/norm
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(eigen_sum3(__fmul_rn(prx, prx), __fmul_rn(pry, pry), __fmul_rn(prz, prz))));
+    prx = __fmul_rn(prx, inv); pry = __fmul_rn(pry, inv); prz = __fmul_rn(prz, inv);
+  }
+  // cross = x_axis x proj
+  const float crx = __fsub_rn(__fmul_rn(axy, prz), __fmul_rn(axz, pry));
+  const float cry = __fsub_rn(__fmul_rn(axz, prx), __fmul_rn(axx, prz));
+  const float crz = __fsub_rn(__fmul_rn(axx, pry), __fmul_rn(axy, prx));
+  const float crn = __fsqrt_rn(eigen_sum3(__fmul_rn(crx, crx), __fmul_rn(cry, cry), __fmul_rn(crz, crz)));
+  const float dt = eigen_sum3(__fmul_rn(axx, prx), __fmul_rn(axy, pry), __fmul_rn(axz, prz));
+  // atan2f / acosf through double so that the float result is (almost always) correctly rounded
+  float phi = __fmul_rn((float)atan2((double)crn, (double)dt), 57.29578f);
+  const float cdn = eigen_sum3(__fmul_rn(crx, 0.0f), __fmul_rn(cry, 0.0f), __fmul_rn(crz, 1.0f));
+  phi = (cdn < 0.f) ? __fsub_rn(360.0f, phi) : phi;
+  float nox = pox, noy = poy, noz = poz;
+  {
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(eigen_sum3(__fmul_rn(nox, nox), __fmul_rn(noy, noy), __fmul_rn(noz, noz))));
+    nox = __fmul_rn(nox, inv); noy = __fmul_rn(noy, inv); noz = __fmul_rn(noz, inv);
+  }
+  float th = eigen_sum3(__fmul_rn(0.0f, nox), __fmul_rn(0.0f, noy), __fmul_rn(1.0f, noz));
+  const float t1 = (-1.0f < th) ? th : -1.0f;  // std::max(-1.0f, theta)
+  const float t2 = (t1 < 1.0f) ? t1 : 1.0f;    // std::min(1.0f, .)
+  th = __fmul_rn((float)acos((double)t2), 57.29578f);
+  int j = 0, k = 0, l = 0;
+#pragma unroll
+  for (int a = 15; a >= 1; a--) if (rr <= P.radii[a]) j = a - 1;
+#pragma unroll
+  for (int a = 11; a >= 1; a--) if (th <= P.theta[a]) k = a - 1;
+#pragma unroll
+  for (int a = 12; a >= 1; a--) if (phi <= P.phi[a]) l = a - 1;
+  bin = l * 165 + k * 15 + j;
+  wgt = __fmul_rn(__fdiv_rn(1.0f, (float)dens), lut[bin]);
+  return true;
+}
+
+// PCL adds the contributions of a keypoint in ascending (squared distance, point index) order
+// (FLANN's sorted radius search), so a bin's float sum depends on that order.  Up to CAP
+// contributions are therefore collected as (key, weight) records with
+//   key = bin << 52 | float_bits(d2) << 20 | point index      (bin < 2048, index < 2^20)
+// grouped by bin with a counting pass (the bin is the major key), ranked inside their bin by
+// counting smaller keys (keys are unique) and summed bin by bin in that order, which makes the
+// descriptor bit-identical to the sequential loop.
+// Work layout per keypoint: one warp finds the spans of all grid rows the search sphere touches
+// (one row per lane), every thread sweeps the flattened candidate range and the true neighbours are
+// compacted into a list, so the expensive bin arithmetic runs on a dense list with no idle lanes.
+// Three instantiations share the keypoints by neighbour count: (NB_MIN, CAP] each; the LAST one also
+// takes keypoints beyond its CAP, whose sums then use shared-memory float atomics (order-free,
+// ~1e-7 relative) and are counted in DevCounters::desc_unordered.
+template <int NT, int CAP, int NB_MIN, bool LAST>
+__global__ void __launch_bounds__(NT) k_desc_hist(
     const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
     int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted,
     const unsigned* __restrict__ sortedKey, const int* __restrict__ rowStart,
     const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
     const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
     float* __restrict__ desc, DevCounters* __restrict__ ctr) {
-  __shared__ float hist[FE_DESC_LEN];
-  __shared__ int s_rank;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keyA = (unsigned long long*)smem_raw;
+  unsigned long long* keyB = keyA + CAP;
+  float* wA = (float*)(keyB + CAP);
+  float* wB = wA + CAP;
+  float* hist = wB + CAP;
+  int* binCnt = (int*)hist;  // the histogram's storage counts records per bin while they are collected
+  unsigned* nbrList = (unsigned*)keyB;  // compacted neighbour positions (consumed before keyB is written)
+  __shared__ int s_rank, s_cnt, s_total;
+  __shared__ int s_scan[40];
+  __shared__ int s_spanB[32], s_spanS[33];
   const int total = kpOff[n_scans];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (int g = blockIdx.x; g < total; g += gridDim.x) {
     float* out = desc + (long long)g * FE_DESC_LEN;
     const int nb = kpNbr[g];
+    if (NB_MIN > 0 && nb <= NB_MIN) continue;  // a smaller instantiation's keypoint
+    if (!LAST && nb > CAP) continue;           // a larger instantiation's keypoint
     if (nb == 0) {  // no neighbour (or non-finite keypoint): descriptor is NaN (3dsc.hpp)
-      for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) out[i] = __int_as_float(0x7fc00000);
+      for (int i = tid; i < FE_DESC_LEN; i += NT) out[i] = __int_as_float(0x7fc00000);
       continue;
     }
+    const bool ordered = nb <= CAP;
     const int s = kpScan[g];
-    for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) hist[i] = 0.0f;
-    if (threadIdx.x == 0) s_rank = 0;
+    for (int i = tid; i < FE_DESC_LEN; i += NT) hist[i] = 0.0f;
+    if (tid == 0) { s_rank = 0; s_cnt = 0; if (!ordered) atomicAdd(&ctr->desc_unordered, 1); }
     __syncthreads();
     // the RNG is consumed only by keypoints that have neighbours, in keypoint order
     {
       int c = 0;
-      for (int j = kpOff[s] + threadIdx.x; j < g; j += blockDim.x) c += (kpNbr[j] > 0) ? 1 : 0;
+      for (int j = kpOff[s] + tid; j < g; j += NT) c += (kpNbr[j] > 0) ? 1 : 0;
 #pragma unroll
       for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FE_FULL, c, d);
       if (lane == 0 && c) atomicAdd(&s_rank, c);
@@ -1313,13 +1441,12 @@ __global__ void __launch_bounds__(256) k_desc_hist(
     __syncthreads();
     const int rank = s_rank;
     if (rank >= axesCap) {
-      if (threadIdx.x == 0) atomicOr(&ctr->err, ERR_AXIS_CAP);
-      for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) out[i] = __int_as_float(0x7fc00000);
+      if (tid == 0) atomicOr(&ctr->err, ERR_AXIS_CAP);
+      for (int i = tid; i < FE_DESC_LEN; i += NT) out[i] = __int_as_float(0x7fc00000);
       __syncthreads();
       continue;
     }
     const float2 ax = axes[rank];  // normalised x_axis = (ax.x, ax.y, -0)
-    const float axz = -0.0f;
     const float4 o = kpOut[g];
     const long long base = scan_off[s];
     const float4* so = sorted + base;
@@ -1328,60 +1455,125 @@ __global__ void __launch_bounds__(256) k_desc_hist(
     const int* rh = rho + base;
     const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
-    for (int r = cy0 + w; r <= cy1; r += 8) {
-      int b, e;
-      row_span(sk, rs, r, cx0, cx1, P.sg_bx, b, e);
-      for (int i = b + lane; i < e; i += 32) {
+    for (int r0 = cy0; r0 <= cy1; r0 += 32) {  // at most ~12 rows: one pass
+      if (w == 0) {
+        int b = 0, e = 0;
+        if (r0 + lane <= cy1) row_span(sk, rs, r0 + lane, cx0, cx1, P.sg_bx, b, e);
+        int inc = e - b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(FE_FULL, inc, d);
+          if (lane >= d) inc += t;
+        }
+        s_spanB[lane] = b;
+        s_spanS[lane] = inc - (e - b);
+        if (lane == 31) { s_spanS[32] = inc; s_total = inc; }
+      }
+      __syncthreads();
+      const int ncand = s_total;
+      for (int t0 = 0; t0 < ncand; t0 += NT) {
+        const int t = t0 + tid;
+        bool isn = false;
+        int i = 0;
+        float d2 = 0.f;
+        if (t < ncand) {
+          int r = 0;
+#pragma unroll
+          for (int k = 16; k; k >>= 1) if (r + k < 32 && s_spanS[r + k] <= t) r += k;
+          i = s_spanB[r] + (t - s_spanS[r]);
+          const float4 q = so[i];
+          d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
+          isn = d2 < P.R2f;
+          if (isn && !ordered) {  // beyond the capacity: order-free accumulation
+            int bin; float wgt;
+            if (shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wgt)) atomicAdd(&hist[bin], wgt);
+          }
+        }
+        if (ordered) {
+          const unsigned m = __ballot_sync(FE_FULL, isn);
+          int basePos = 0;
+          if (lane == 0 && m) basePos = atomicAdd(&s_cnt, __popc(m));
+          basePos = __shfl_sync(FE_FULL, basePos, 0);
+          if (isn) nbrList[basePos + __popc(m & lanemask_lt())] = (unsigned)i;
+        }
+      }
+      __syncthreads();
+    }
+    if (ordered) {
+      const int nl = s_cnt;  // == nb
+      __syncthreads();
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      // dense pass over the neighbours: bin, weight, record
+      for (int t = tid; t < nl; t += NT) {
+        const int i = (int)nbrList[t];
         const float4 q = so[i];
         const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
-        if (!(d2 < P.R2f)) continue;
-        if (fabsf(d2 - 0.0f) < 1.17549435e-38f) continue;  // pcl::utils::equal(nn_dists, 0)
-        const float rr = __fsqrt_rn(d2);
-        // pcl::geometry::project(neighbour, origin, normal=(0,0,1), proj); proj -= origin
-        const float pox = __fsub_rn(q.x, o.x), poy = __fsub_rn(q.y, o.y), poz = __fsub_rn(q.z, o.z);
-        const float lambda = eigen_sum3(__fmul_rn(0.0f, pox), __fmul_rn(0.0f, poy), __fmul_rn(1.0f, poz));
-        float prx = __fsub_rn(__fsub_rn(q.x, __fmul_rn(lambda, 0.0f)), o.x);
-        float pry = __fsub_rn(__fsub_rn(q.y, __fmul_rn(lambda, 0.0f)), o.y);
-        float prz = __fsub_rn(__fsub_rn(q.z, __fmul_rn(lambda, 1.0f)), o.z);
-        {  // Eigen 3.2 normalize(): multiply by 1/norm
-          const float inv = __fdiv_rn(1.0f, __fsqrt_rn(eigen_sum3(__fmul_rn(prx, prx), __fmul_rn(pry, pry), __fmul_rn(prz, prz))));
-          prx = __fmul_rn(prx, inv); pry = __fmul_rn(pry, inv); prz = __fmul_rn(prz, inv);
+        int bin; float wgt;
+        if (shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wgt)) {
+          const int slot = atomicAdd(&s_cnt, 1);
+          keyA[slot] = ((unsigned long long)bin << 52) | ((unsigned long long)__float_as_uint(d2) << 20) |
+                       (unsigned long long)((unsigned)__float_as_int(q.w) & 0xFFFFFu);
+          wA[slot] = wgt;
+          atomicAdd(&binCnt[bin], 1);
         }
-        // cross = x_axis x proj
-        const float crx = __fsub_rn(__fmul_rn(ax.y, prz), __fmul_rn(axz, pry));
-        const float cry = __fsub_rn(__fmul_rn(axz, prx), __fmul_rn(ax.x, prz));
-        const float crz = __fsub_rn(__fmul_rn(ax.x, pry), __fmul_rn(ax.y, prx));
-        const float crn = __fsqrt_rn(eigen_sum3(__fmul_rn(crx, crx), __fmul_rn(cry, cry), __fmul_rn(crz, crz)));
-        const float dt = eigen_sum3(__fmul_rn(ax.x, prx), __fmul_rn(ax.y, pry), __fmul_rn(axz, prz));
-        // atan2f / acosf through double so that the float result is (almost always) correctly rounded
-        float phi = __fmul_rn((float)atan2((double)crn, (double)dt), 57.29578f);
-        const float cdn = eigen_sum3(__fmul_rn(crx, 0.0f), __fmul_rn(cry, 0.0f), __fmul_rn(crz, 1.0f));
-        phi = (cdn < 0.f) ? __fsub_rn(360.0f, phi) : phi;
-        float nox = pox, noy = poy, noz = poz;
-        {
-          const float inv = __fdiv_rn(1.0f, __fsqrt_rn(eigen_sum3(__fmul_rn(nox, nox), __fmul_rn(noy, noy), __fmul_rn(noz, noz))));
-          nox = __fmul_rn(nox, inv); noy = __fmul_rn(noy, inv); noz = __fmul_rn(noz, inv);
-        }
-        float th = eigen_sum3(__fmul_rn(0.0f, nox), __fmul_rn(0.0f, noy), __fmul_rn(1.0f, noz));
-        const float t1 = (-1.0f < th) ? th : -1.0f;  // std::max(-1.0f, theta)
-        const float t2 = (t1 < 1.0f) ? t1 : 1.0f;    // std::min(1.0f, .)
-        th = __fmul_rn((float)acos((double)t2), 57.29578f);
-        int j = 0, k = 0, l = 0;
-#pragma unroll
-        for (int a = 15; a >= 1; a--) if (rr <= P.radii[a]) j = a - 1;
-#pragma unroll
-        for (int a = 11; a >= 1; a--) if (th <= P.theta[a]) k = a - 1;
-#pragma unroll
-        for (int a = 12; a >= 1; a--) if (phi <= P.phi[a]) l = a - 1;
-        const int dens = rh[i];
-        if (dens <= 0) continue;
-        const int bin = l * 165 + k * 15 + j;
-        const float wgt = __fmul_rn(__fdiv_rn(1.0f, (float)dens), lut[bin]);
-        atomicAdd(&hist[bin], wgt);
       }
+      __syncthreads();
+      const int n = s_cnt;
+      // (1) exclusive scan of the per-bin counts -> first slot of every bin
+      {
+        constexpr int PER = (FE_DESC_LEN + NT - 1) / NT;
+        int loc[PER];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+          const int bi = tid * PER + k;
+          loc[k] = (bi < FE_DESC_LEN) ? binCnt[bi] : 0;
+          sum += loc[k];
+        }
+        int tot;
+        int run = block_excl_scan<NT>(sum, &tot, s_scan);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+          const int bi = tid * PER + k;
+          if (bi < FE_DESC_LEN) binCnt[bi] = run;
+          run += loc[k];
+        }
+      }
+      __syncthreads();
+      // (2) group the records by bin (order inside a bin still arbitrary)
+      for (int i = tid; i < n; i += NT) {
+        const unsigned long long k = keyA[i];
+        const int pos = atomicAdd(&binCnt[(int)(k >> 52)], 1);
+        keyB[pos] = k;
+        wB[pos] = wA[i];
+      }
+      __syncthreads();
+      // (3) rank every record inside its bin: position = bin start + number of smaller keys
+      for (int i = tid; i < n; i += NT) {
+        const unsigned long long k = keyB[i];
+        const unsigned bin = (unsigned)(k >> 52);
+        int smaller = 0, left = 0;
+        for (int t = i - 1; t >= 0 && (unsigned)(keyB[t] >> 52) == bin; t--) { left++; smaller += (keyB[t] < k) ? 1 : 0; }
+        for (int t = i + 1; t < n && (unsigned)(keyB[t] >> 52) == bin; t++) smaller += (keyB[t] < k) ? 1 : 0;
+        const int pos = i - left + smaller;
+        keyA[pos] = k;
+        wA[pos] = wB[i];
+      }
+      for (int i = tid; i < FE_DESC_LEN; i += NT) hist[i] = 0.0f;  // the counters are no longer needed
+      __syncthreads();
+      // (4) sum every bin in order
+      for (int i = tid; i < n; i += NT) {
+        const unsigned bin = (unsigned)(keyA[i] >> 52);
+        if (i == 0 || (unsigned)(keyA[i - 1] >> 52) != bin) {
+          float acc = 0.0f;
+          for (int t = i; t < n && (unsigned)(keyA[t] >> 52) == bin; t++) acc = __fadd_rn(acc, wA[t]);
+          hist[bin] = acc;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < FE_DESC_LEN; i += blockDim.x) out[i] = hist[i];
+    for (int i = tid; i < FE_DESC_LEN; i += NT) out[i] = hist[i];
     __syncthreads();
   }
 }

@@ -282,10 +282,10 @@ class FeatureExtractionNode:
         return float(ms.value)
 
     def batchStats(self):
-        out = np.zeros(8, np.int64)
+        out = np.zeros(10, np.int64)
         self._check(N.lib().fe_get_batch_stats(self._ctx, _ptr(out)))
         keys = ("points", "surface_points", "crop_points", "ring_clusters", "keypoints", "neighbours",
-                "deferred_ring_scans", "deferred_merge_scans")
+                "deferred_ring_scans", "deferred_merge_scans", "deferred_surface_scans", "descriptors_unordered")
         return dict(zip(keys, (int(v) for v in out)))
 
     def stageTimes(self):

@@ -149,9 +149,10 @@ int fe_timer_begin(fe_ctx_t* ctx);
 int fe_timer_end(fe_ctx_t* ctx, float* elapsed_ms);
 
 /* Work counters of the last fe_process_batch_device call (for roofline arithmetic):
- * out[0..7] = points, surface points kept, cropped points, ring clusters (keypoints_full),
- * keypoints, sum of 3DSC neighbours, scans deferred to the large K2, scans deferred to the large K3. */
-int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[8]);
+ * out[0..9] = points, surface points kept, cropped points, ring clusters (keypoints_full),
+ * keypoints, sum of 3DSC neighbours, scans deferred to the large K2, to the large K3, to the
+ * global-memory K4a, keypoints whose descriptor was summed out of PCL's order (> 8192 contributions). */
+int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[10]);
 
 /* Per-kernel CUDA-event times (ms) of the last device call; names are static strings. */
 int fe_get_stage_times(fe_ctx_t* ctx, int32_t cap, const char** names, float* ms, int32_t* n);

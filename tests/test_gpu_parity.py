@@ -160,3 +160,24 @@ def test_record_layouts_decode_on_device(ob, synth, nodes, stride, offs):
     assert np.array_equal(ko, ko2) and bits_equal(kp, kp2)
     from util import rel_err
     assert rel_err(d2, d).max() < 1e-5
+
+
+@pytest.mark.parametrize("cfg,nscans", [(1, 3), (2, 12), (3, 1), (4, 2)])
+def test_descriptors_are_bit_identical_when_summed_in_pcl_order(ob, synth, nodes, cfg, nscans):
+    """Rows J/N: the contributions of a keypoint are added in ascending (d2, index) order like
+    FLANN's sorted radius search delivers them, so the float sums are the oracle's bit for bit
+    (keypoints with more than 8192 contributions use order-free atomics and only meet the 1e-5 bar)."""
+    P = _params(ob, cfg)
+    nd = nodes(cfg)
+    pts, offs, rp = synth.generate(cfg, nscans, scan_index_base=300)
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    exact = total = 0
+    for s in range(nscans):
+        r = ob.process_scan(P, pts[offs[s]:offs[s + 1]], rp[s, 0], rp[s, 1], mode=0)
+        dg = d[ko[s]:ko[s + 1]]
+        assert bits_equal(kp[ko[s]:ko[s + 1]], r["keypoints"])
+        for i in range(len(dg)):
+            if r["n_neighbors"][i] <= 8192 and r["edge_margin"][i] > 2e-6:
+                total += 1
+                exact += int(bits_equal(dg[i], r["descriptors"][i]))
+    assert total > 0 and exact == total, (exact, total)
