@@ -425,10 +425,10 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), s.stream));
   if (nch > 0 && k1flags >= 0) {
     if (lay.raw)
-      k_level_crop_ring<true><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+      k_level_crop_ring<true, true><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
                                                          s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
     else
-      k_level_crop_ring<false><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+      k_level_crop_ring<false, true><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
                                                           s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
     ctx->launches++;
   }
@@ -909,7 +909,7 @@ static int stage_k1(fe_ctx* ctx, fe_point_t* cloud, int64_t n, double roll, doub
   st = stage_scans(ctx, s, offs, rp, 1, &npts, &nch);
   if (st) return st;
   CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
-  k_level_crop_ring<false><<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+  k_level_crop_ring<false, false><<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
                                                s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full, RawLayout{nullptr, 0, 0, 0, 0});
   ctx->launches++;
   CK(cudaGetLastError());
@@ -944,7 +944,7 @@ static int stage_upload_k1(fe_ctx* ctx, Slot& s, const fe_point_t* in, int64_t n
   if (st) return st;
   if (n > 0) CK(cudaMemcpyAsync(s.d_pts, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   if (*nchOut > 0) {
-    k_level_crop_ring<false><<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+    k_level_crop_ring<false, false><<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
                                                      s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, RawLayout{nullptr, 0, 0, 0, 0});
     ctx->launches++;
   }

@@ -143,13 +143,15 @@ struct RawLayout {  // records of fe_point_layout_t; raw == nullptr: the input i
 // the chunk's own slot of the output arrays (same CSR as the input) with their counts, so the
 // per-scan consumers concatenate pieces in order and no global prefix sum is needed.
 // ============================================================================================
-template <bool RAW>
+template <bool RAW, bool FUSED>
 __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
     const float4* __restrict__ pts, const long long* __restrict__ scan_off,
     const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
-    int flags, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
+    int flags_rt, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
     unsigned* __restrict__ cropMeta, int* __restrict__ cropCnt, float4* __restrict__ full_out,
     RawLayout L) {
+  // FUSED: the cloudCallback path, every stage on (surface stream optional); otherwise run-time flags
+  const int flags = FUSED ? (F_ELEV | F_ROT | F_CROP | F_RING | (flags_rt & F_SURF)) : flags_rt;
   __shared__ int s_scan;
   __shared__ int s_ws[8], s_wc[8];
   const int chunk = blockIdx.x;
@@ -189,7 +191,6 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
         p = __ldg(pts + base + j);
       }
       float el = p.w;
-      if (flags & F_ELEV) el = elevation_deg(p.x, p.y, p.z);  // getElevationAngles, src:147-156
       if (flags & F_ROT) {
         // pcl::transformPointCloud, PCL 1.8.0 scalar form: left to right, unfused, + translation 0
         q.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], p.x), __fmul_rn(m[1], p.y)), __fmul_rn(m[2], p.z)), 0.0f);
@@ -198,14 +199,17 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
       } else {
         q.x = p.x; q.y = p.y; q.z = p.z;
       }
-      q.w = el;
-      if (full_out) full_out[base + j] = q;
       const bool fin = finite3(q.x, q.y, q.z);
       // pcl::PassThrough: non-finite dropped, inclusive float limits (src:169-183)
       fc = fin;
       if (flags & F_CROP)
         fc = fin && !(q.z < P.zmin || q.z > P.zmax) && !(q.y < P.ymin || q.y > P.ymax) &&
              !(q.x < P.xmin || q.x > P.xmax);
+      // getElevationAngles, src:147-156.  The angle only travels with the cropped cloud (the
+      // descriptor surface never reads it), so it is evaluated for the crop survivors alone.
+      if ((flags & F_ELEV) && (fc || (!FUSED && full_out))) el = elevation_deg(p.x, p.y, p.z);
+      q.w = el;
+      if (!FUSED && full_out) full_out[base + j] = q;
       if (fc) {
         unsigned rm = 1u;
         if (flags & F_RING) {
