@@ -220,11 +220,13 @@ def main():
         return float(t.item())
 
     # ---- value: device-resident hot path ----
+    # clocks / throttle reasons are sampled from before the warm-up to the end of the e2e phase (the
+    # device-resident timed region alone is shorter than one nvidia-smi sampling period)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches = 0
     stage_acc = {}
     dev_node.timerBegin()
@@ -237,7 +239,6 @@ def main():
     ev_ms = dev_node.timerEnd()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
     ms_step = max_over_ranks(ev_ms / args.steps)
     value = world * B / (ms_step * 1e-3)
     stats = dev_node.batchStats()
@@ -302,6 +303,7 @@ def main():
     same12 = bool(np.array_equal(ko12, ko) and np.array_equal(kp12.view(np.uint32), kp.view(np.uint32)))
     ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)  # leave the float4 results in place for the checks below
     pin12.free()
+    clocks = sampler.stop()
     h2d = npts * 16 + (B + 1) * 12 + B * 36
     d2h = int(len(kp)) * 16 + (0 if d is None else int(len(kp)) * 1980 * 4) + (B + 1) * 4 + 32
 

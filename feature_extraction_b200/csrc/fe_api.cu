@@ -33,7 +33,7 @@ struct Slot {
   int *d_kfBase = nullptr, *d_kfCnt = nullptr, *d_kcBase = nullptr, *d_kcCnt = nullptr;
   int *d_kpBase = nullptr, *d_kpCnt = nullptr, *d_kpOff = nullptr, *d_kpScan = nullptr, *d_kpNbr = nullptr;
   int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
-  int *d_ovfRings = nullptr, *d_ovfMerge = nullptr, *d_ovfSurf = nullptr;
+  int *d_ovfRings = nullptr, *d_ovfRings2 = nullptr, *d_ovfMerge = nullptr, *d_ovfSurf = nullptr;
   int64_t capRowStart = 0;
   float4 *d_kfPool = nullptr, *d_kcPool = nullptr, *d_kpPool = nullptr, *d_kpOut = nullptr, *d_gather = nullptr;
   float* d_desc = nullptr;
@@ -216,7 +216,7 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfMerge, s.d_ovfSurf, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfSurf, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
   for (void* p : hv) if (p) cudaFreeHost(p);
@@ -258,7 +258,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_kpBase, ns)); CK(dalloc(&s.d_kpCnt, ns)); CK(dalloc(&s.d_kpOff, ns + 1));
   CK(dalloc(&s.d_kpScan, (size_t)s.capKp)); CK(dalloc(&s.d_kpNbr, (size_t)s.capKp));
   CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1));
-  CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfSurf, ns));
+  CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfRings2, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfSurf, ns));
   CK(dalloc(&s.d_kfPool, (size_t)s.capKf)); CK(dalloc(&s.d_kpPool, (size_t)s.capKp)); CK(dalloc(&s.d_kpOut, (size_t)s.capKp));
   CK(dalloc(&s.d_desc, (size_t)s.capKp * FE_DESC_LEN));
   CK(dalloc(&s.d_ctr, 1));
@@ -339,6 +339,7 @@ int ensure_kc(fe_ctx* ctx, Slot& s) {
 
 const size_t kClusterSmem = cluster_smem_bytes(ECAP, NTF);
 const size_t kClusterSmemL = cluster_smem_bytes(ECAP_L, NT2);
+const size_t kClusterSmemMD = cluster_smem_bytes(ECAP_MD, NT2);
 const size_t kClusterSmemM = cluster_smem_bytes(ECAP_M, NTM);
 
 int set_kernel_attrs(fe_ctx* ctx) {
@@ -397,12 +398,15 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
   float4* kc = wantKc ? s.d_kcPool : nullptr;
   int* kcB = wantKc ? s.d_kcBase : nullptr;
   int* kcC = wantKc ? s.d_kcCnt : nullptr;
-  k_cluster_rings<ECAP, NTF, 4><<<nscans, NTF, kClusterSmem, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
-                                                                    singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
-                                                                    s.capKc, kcB, kcC, s.d_ctr, nullptr, nullptr, s.d_ovfRings);
-  k_cluster_rings<ECAP_L, NT2, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P,
-                                                                      singleRing ? 1 : 0, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
-                                                                      s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr);
+  const int sr = singleRing ? 1 : 0;
+  k_cluster_rings<ECAP, NTF, 4><<<nscans, NTF, kClusterSmem, s.stream>>>(
+      s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc,
+      kcB, kcC, s.d_ctr, nullptr, nullptr, s.d_ovfRings, ovfR);
+  // (a 2-blocks-per-SM middle instantiation was measured and lost: dense scans need more ring groups
+  //  there and mostly cascade to the large one anyway)
+  k_cluster_rings<ECAP_L, NT2, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(
+      s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc,
+      kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr, nullptr);
   ctx->launches += 2;
   if (marks) mark(ctx, s, "K2 ring clusters");
   if (merge) {
@@ -880,7 +884,7 @@ int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[10]) {
       for (int v : nb) out[5] += v;
     }
   }
-  out[6] = s.h_ctr->ovf_rings;
+  out[6] = s.h_ctr->ovf_rings;  // (of which ovf_rings2 went on to the large instantiation)
   out[7] = s.h_ctr->ovf_merge;
   out[8] = s.h_ctr->ovf_surf;
   out[9] = s.h_ctr->desc_unordered;

@@ -28,6 +28,7 @@ constexpr int ECAP = 1408;      // cluster entries of the fast instantiation (25
 constexpr int NTF = 256;
 constexpr int ECAP_M = 512;     // K3 fast instantiation: ring centroids per scan (64 threads, many blocks / SM)
 constexpr int NTM = 64;
+constexpr int ECAP_MD = 2944;   // K2 medium instantiation (512 threads, 2 blocks / SM) for denser scans
 constexpr int ECAP_L = 6528;    // the large instantiation (512 threads, 1 block / SM) for scans the fast one defers
 
 // error bits reported through DevCounters::err
@@ -71,11 +72,12 @@ struct DevCounters {
   int kc_cursor;   // keypoint_cloud pool
   int err;
   int kp_total;
-  int ovf_rings;   // scans deferred from K2 to its large instantiation
+  int ovf_rings;   // scans deferred from the fast K2 to the medium instantiation
+  int ovf_rings2;  // scans deferred from the medium K2 to the large instantiation
   int ovf_merge;   // scans deferred from K3 to its large instantiation
   int ovf_surf;    // scans deferred from the shared-memory K4a to the global-memory one
-  int desc_unordered;  // keypoints with more than DCAP contributions (summed with atomics, not in PCL's order)
-  int pad[3];
+  int desc_unordered;  // keypoints with more than DCAP_L contributions (summed with atomics, not in PCL's order)
+  int pad[2];
 };
 
 // getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
@@ -676,7 +678,7 @@ __device__ void cluster_rings_scan(
     const int* __restrict__ chunk_off, const DevParams& P, int single_ring,
     float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
     float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
-    DevCounters* __restrict__ ctr, int* __restrict__ ovfList) {
+    DevCounters* __restrict__ ctr, int* __restrict__ ovfList, int* __restrict__ ovfCount) {
   const int tid = threadIdx.x;
   int* pre = S.misc;
   int* sc = S.misc + MAXCHUNK + 1;
@@ -704,7 +706,7 @@ __device__ void cluster_rings_scan(
     for (int r = 0; r < nRingsAll; r++) big = max(big, ringCnt[r]);
     if (big > CAP) {  // a single ring is larger than this instantiation's capacity
       if (tid == 0) {
-        if (ovfList) ovfList[atomicAdd(&ctr->ovf_rings, 1)] = s;  // the large instantiation takes it
+        if (ovfList) ovfList[atomicAdd(ovfCount, 1)] = s;  // the next larger instantiation takes it
         else atomicOr(&ctr->err, ERR_RING_CAP);
       }
       return;
@@ -842,19 +844,19 @@ __global__ void __launch_bounds__(NT, MINB) k_cluster_rings(
     float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
     float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
     DevCounters* __restrict__ ctr, const int* __restrict__ scanList, const int* __restrict__ nList,
-    int* __restrict__ ovfList) {
+    int* __restrict__ ovfList, int* __restrict__ ovfCount) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
   cluster_sm_carve<CAP, NT>(smem_raw, S);
   if (!scanList) {
     cluster_rings_scan<CAP, NT>(S, blockIdx.x, crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
-                            kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfList);
+                            kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfList, ovfCount);
   } else {
     const int n = *nList;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
       __syncthreads();
       cluster_rings_scan<CAP, NT>(S, scanList[i], crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
-                              kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, nullptr);
+                              kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfList, ovfCount);
     }
   }
 }
