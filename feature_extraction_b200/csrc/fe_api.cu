@@ -339,13 +339,13 @@ int ensure_kc(fe_ctx* ctx, Slot& s) {
 
 const size_t kClusterSmem = cluster_smem_bytes(ECAP, NTF);
 const size_t kClusterSmemL = cluster_smem_bytes(ECAP_L, NT2);
-const size_t kClusterSmemMD = cluster_smem_bytes(ECAP_MD, NT2);
+const size_t kClusterSmemL2 = cluster_smem_bytes(ECAP_L, NTL);
 const size_t kClusterSmemM = cluster_smem_bytes(ECAP_M, NTM);
 
 int set_kernel_attrs(fe_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
-  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NTL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL2));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_desc_hist<256, DCAP, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)desc_smem_bytes(DCAP, 256)));
@@ -404,7 +404,7 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
       kcB, kcC, s.d_ctr, nullptr, nullptr, s.d_ovfRings, ovfR);
   // (a 2-blocks-per-SM middle instantiation was measured and lost: dense scans need more ring groups
   //  there and mostly cascade to the large one anyway)
-  k_cluster_rings<ECAP_L, NT2, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(
+  k_cluster_rings<ECAP_L, NTL, 1><<<gridL, NTL, kClusterSmemL2, s.stream>>>(
       s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc,
       kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr, nullptr);
   ctx->launches += 2;

@@ -28,8 +28,9 @@ constexpr int ECAP = 1408;      // cluster entries of the fast instantiation (25
 constexpr int NTF = 256;
 constexpr int ECAP_M = 512;     // K3 fast instantiation: ring centroids per scan (64 threads, many blocks / SM)
 constexpr int NTM = 64;
+constexpr int NTL = 1024;      // threads of the large K2 instantiation
 constexpr int ECAP_MD = 2944;   // K2 medium instantiation (512 threads, 2 blocks / SM) for denser scans
-constexpr int ECAP_L = 6528;    // the large instantiation (512 threads, 1 block / SM) for scans the fast one defers
+constexpr int ECAP_L = 6144;    // the large instantiations (1 block / SM) for scans the fast ones defer
 
 // error bits reported through DevCounters::err
 enum {
