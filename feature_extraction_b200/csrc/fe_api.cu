@@ -33,7 +33,8 @@ struct Slot {
   int *d_kfBase = nullptr, *d_kfCnt = nullptr, *d_kcBase = nullptr, *d_kcCnt = nullptr;
   int *d_kpBase = nullptr, *d_kpCnt = nullptr, *d_kpOff = nullptr, *d_kpScan = nullptr, *d_kpNbr = nullptr;
   int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
-  int *d_ovfRings = nullptr, *d_ovfRings2 = nullptr, *d_ovfMerge = nullptr, *d_ovfSurf = nullptr;
+  int *d_ovfRings = nullptr, *d_ovfRings2 = nullptr, *d_ovfMerge = nullptr, *d_ovfMerge2 = nullptr, *d_ovfSurf = nullptr;
+  unsigned char* d_slabs = nullptr;
   int64_t capRowStart = 0;
   float4 *d_kfPool = nullptr, *d_kcPool = nullptr, *d_kpPool = nullptr, *d_kpOut = nullptr, *d_gather = nullptr;
   float* d_desc = nullptr;
@@ -216,7 +217,7 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfSurf, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
   for (void* p : hv) if (p) cudaFreeHost(p);
@@ -258,7 +259,9 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_kpBase, ns)); CK(dalloc(&s.d_kpCnt, ns)); CK(dalloc(&s.d_kpOff, ns + 1));
   CK(dalloc(&s.d_kpScan, (size_t)s.capKp)); CK(dalloc(&s.d_kpNbr, (size_t)s.capKp));
   CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1));
-  CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfRings2, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfSurf, ns));
+  CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfRings2, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfMerge2, ns));
+  CK(dalloc(&s.d_ovfSurf, ns));
+  CK(dalloc(&s.d_slabs, (size_t)NGLOBAL * cluster_slab_bytes(ECAP_G)));
   CK(dalloc(&s.d_kfPool, (size_t)s.capKf)); CK(dalloc(&s.d_kpPool, (size_t)s.capKp)); CK(dalloc(&s.d_kpOut, (size_t)s.capKp));
   CK(dalloc(&s.d_desc, (size_t)s.capKp * FE_DESC_LEN));
   CK(dalloc(&s.d_ctr, 1));
@@ -343,11 +346,11 @@ const size_t kClusterSmemL2 = cluster_smem_bytes(ECAP_L, NTL);
 const size_t kClusterSmemM = cluster_smem_bytes(ECAP_M, NTM);
 
 int set_kernel_attrs(fe_ctx* ctx) {
-  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
-  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NTL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL2));
-  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
-  CK(cudaFuncSetAttribute(k_extract_clusters_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NTL, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL2));
+  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
+  CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
+  CK(cudaFuncSetAttribute(k_extract_clusters_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_desc_hist<256, DCAP, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)desc_smem_bytes(DCAP, 256)));
   CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_M, DCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)desc_smem_bytes(DCAP_M, 512)));
@@ -391,33 +394,38 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
 void mark(fe_ctx* ctx, Slot& s, const char* name);
 
 void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool wantKc, bool merge, bool marks = false) {
+  // Every stage is a chain of instantiations: the fast one takes all scans and defers those that do
+  // not fit its shared memory to a list; the large shared-memory one takes that list; what does not
+  // fit there either goes to the instantiation whose per-entry arrays live in global memory.
   const DevParams& P = ctx->dp;
-  const int gridL = std::min(nscans, 148);
+  const int gridL = std::min(nscans, 148), gridG = std::min(nscans, NGLOBAL);
+  const size_t smemG = cluster_smem_bytes_global(NT2);
   int* ovfR = &s.d_ctr->ovf_rings;
+  int* ovfR2 = &s.d_ctr->ovf_rings2;
   int* ovfM = &s.d_ctr->ovf_merge;
+  int* ovfM2 = &s.d_ctr->ovf_merge2;
   float4* kc = wantKc ? s.d_kcPool : nullptr;
   int* kcB = wantKc ? s.d_kcBase : nullptr;
   int* kcC = wantKc ? s.d_kcCnt : nullptr;
   const int sr = singleRing ? 1 : 0;
-  k_cluster_rings<ECAP, NTF, 4><<<nscans, NTF, kClusterSmem, s.stream>>>(
-      s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc,
-      kcB, kcC, s.d_ctr, nullptr, nullptr, s.d_ovfRings, ovfR);
-  // (a 2-blocks-per-SM middle instantiation was measured and lost: dense scans need more ring groups
-  //  there and mostly cascade to the large one anyway)
-  k_cluster_rings<ECAP_L, NTL, 1><<<gridL, NTL, kClusterSmemL2, s.stream>>>(
-      s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc,
-      kcB, kcC, s.d_ctr, s.d_ovfRings, ovfR, nullptr, nullptr);
-  ctx->launches += 2;
+#define FE_K2_ARGS s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, \
+                   s.capKc, kcB, kcC, s.d_ctr
+  k_cluster_rings<ECAP, NTF, 4, false><<<nscans, NTF, kClusterSmem, s.stream>>>(FE_K2_ARGS, nullptr, nullptr, s.d_ovfRings, ovfR, nullptr);
+  k_cluster_rings<ECAP_L, NTL, 1, false><<<gridL, NTL, kClusterSmemL2, s.stream>>>(FE_K2_ARGS, s.d_ovfRings, ovfR, s.d_ovfRings2, ovfR2, nullptr);
+  k_cluster_rings<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K2_ARGS, s.d_ovfRings2, ovfR2, nullptr, nullptr, s.d_slabs);
+#undef FE_K2_ARGS
+  ctx->launches += 3;
   if (marks) mark(ctx, s, "K2 ring clusters");
   if (merge) {
-    k_merge_keypoints<ECAP_M, NTM, 8><<<nscans, NTM, kClusterSmemM, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool,
-                                                                                (int)s.capKp, s.d_kpBase, s.d_kpCnt, s.d_ctr, nullptr,
-                                                                                nullptr, s.d_ovfMerge);
-    k_merge_keypoints<ECAP_L, NT2, 1><<<gridL, NT2, kClusterSmemL, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp,
-                                                                          s.d_kpBase, s.d_kpCnt, s.d_ctr, s.d_ovfMerge, ovfM, nullptr);
-    ctx->launches += 2;
+#define FE_K3_ARGS s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp, s.d_kpBase, s.d_kpCnt, s.d_ctr
+    k_merge_keypoints<ECAP_M, NTM, 8, false><<<nscans, NTM, kClusterSmemM, s.stream>>>(FE_K3_ARGS, nullptr, nullptr, s.d_ovfMerge, ovfM, nullptr);
+    k_merge_keypoints<ECAP_L, NT2, 1, false><<<gridL, NT2, kClusterSmemL, s.stream>>>(FE_K3_ARGS, s.d_ovfMerge, ovfM, s.d_ovfMerge2, ovfM2, nullptr);
+    k_merge_keypoints<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K3_ARGS, s.d_ovfMerge2, ovfM2, nullptr, nullptr, s.d_slabs);
+#undef FE_K3_ARGS
+    ctx->launches += 3;
   }
 }
+
 
 // Enqueue the kernels of one sub-batch whose points are at d_pts.  k1flags selects what K1 does;
 // `fromStage`: 0 = K1 first; 1 = crop/cropMeta/cropCnt already filled by the caller.
@@ -992,7 +1000,7 @@ int fe_extract_clusters(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, doubl
   *n_clusters = 0;
   cluster_offsets[0] = 0;
   if (n == 0) return FE_OK;
-  if (n > ECAP_L) return fail(ctx, FE_ERR_CAPACITY, "fe_extract_clusters: cloud larger than the per-block capacity");
+  if (n > ECAP_G) return fail(ctx, FE_ERR_CAPACITY, "fe_extract_clusters: more than 65535 points");
   if (!(tolerance > 0.0)) return fail(ctx, FE_ERR_INVALID, "tolerance must be > 0");
   Slot& s = ctx->slot[0];
   int st = ensure_slot(ctx, s, true);
@@ -1003,7 +1011,12 @@ int fe_extract_clusters(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, doubl
   int* d_off = (int*)s.d_keyA;
   int* d_idx = (int*)s.d_keyB;
   int* d_n = (int*)s.d_valA;
-  k_extract_clusters_stage<<<1, NT2, kClusterSmemL, s.stream>>>(s.d_pts, (int)n, tol_f, r2f, min_size, max_size, d_off, (int)n, d_idx, d_n);
+  if (n <= ECAP_L)
+    k_extract_clusters_stage<false><<<1, NT2, kClusterSmemL, s.stream>>>(s.d_pts, (int)n, tol_f, r2f, min_size, max_size, d_off, (int)n,
+                                                                         d_idx, d_n, nullptr);
+  else
+    k_extract_clusters_stage<true><<<1, NT2, cluster_smem_bytes_global(NT2), s.stream>>>(s.d_pts, (int)n, tol_f, r2f, min_size, max_size,
+                                                                                          d_off, (int)n, d_idx, d_n, s.d_slabs);
   ctx->launches++;
   CK(cudaGetLastError());
   int nc = 0;

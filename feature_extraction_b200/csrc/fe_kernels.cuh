@@ -29,6 +29,8 @@ constexpr int NTF = 256;
 constexpr int ECAP_M = 512;     // K3 fast instantiation: ring centroids per scan (64 threads, many blocks / SM)
 constexpr int NTM = 64;
 constexpr int NTL = 1024;      // threads of the large K2 instantiation
+constexpr int ECAP_G = 65535;   // last resort: per-entry arrays in a global-memory slab (16-bit entry indices)
+constexpr int NGLOBAL = 32;     // blocks (and slabs) of the global-memory instantiations
 constexpr int ECAP_MD = 2944;   // K2 medium instantiation (512 threads, 2 blocks / SM) for denser scans
 constexpr int ECAP_L = 6144;    // the large instantiations (1 block / SM) for scans the fast ones defer
 
@@ -74,11 +76,12 @@ struct DevCounters {
   int err;
   int kp_total;
   int ovf_rings;   // scans deferred from the fast K2 to the medium instantiation
-  int ovf_rings2;  // scans deferred from the medium K2 to the large instantiation
+  int ovf_rings2;  // scans deferred from the large K2 to the global-memory instantiation
   int ovf_merge;   // scans deferred from K3 to its large instantiation
   int ovf_surf;    // scans deferred from the shared-memory K4a to the global-memory one
   int desc_unordered;  // keypoints with more than DCAP_L contributions (summed with atomics, not in PCL's order)
-  int pad[2];
+  int ovf_merge2;      // scans deferred from the large K3 to the global-memory instantiation
+  int pad[1];
 };
 
 // getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
@@ -314,6 +317,29 @@ __device__ __forceinline__ void cluster_sm_carve(unsigned char* p, ClusterSm& S)
   S.lst = (unsigned short*)p; p += CAP * 2;
   S.wc = (unsigned short*)p; p += (NT / 32) * 257 * 2;
   S.ring = (unsigned char*)p;
+}
+
+// Same workspace with the per-entry arrays in a global-memory slab (entries up to ECAP_G); only the
+// radix counters and the small scratch stay in shared memory.
+__host__ __device__ constexpr size_t cluster_slab_bytes(int cap) { return ((size_t)cap * 33 + 255) / 256 * 256; }
+constexpr size_t cluster_smem_bytes_global(int nt) { return (size_t)(nt / 32) * 257 * 2 + (256 + 32) * 4 + MISC_INTS * 4 + 64; }
+
+template <int CAP, int NT>
+__device__ __forceinline__ void cluster_carve_global(unsigned char* g, unsigned char* p, ClusterSm& S) {
+  S.x = (float*)g; g += (size_t)CAP * 4;
+  S.y = (float*)g; g += (size_t)CAP * 4;
+  S.z = (float*)g; g += (size_t)CAP * 4;
+  S.gref = (unsigned*)g; g += (size_t)CAP * 4;
+  S.keyA = (unsigned*)g; g += (size_t)CAP * 4;
+  S.keyB = (unsigned*)g; g += (size_t)CAP * 4;
+  S.valA = (unsigned short*)g; g += (size_t)CAP * 2;
+  S.valB = (unsigned short*)g; g += (size_t)CAP * 2;
+  S.aux = (unsigned short*)g; g += (size_t)CAP * 2;
+  S.lst = (unsigned short*)g; g += (size_t)CAP * 2;
+  S.ring = (unsigned char*)g;
+  S.base = (unsigned*)p; p += (256 + 32) * 4;
+  S.misc = (int*)p; p += MISC_INTS * 4;
+  S.wc = (unsigned short*)p;
 }
 
 struct ClusterOut {
@@ -837,7 +863,7 @@ __device__ void cluster_rings_scan(
 
 // scanList == nullptr: block b handles scan b and defers oversized scans to ovfList;
 // otherwise the blocks loop over scanList[0 .. *nList) (the deferred scans).
-template <int CAP, int NT, int MINB>
+template <int CAP, int NT, int MINB, bool GLOBAL>
 __global__ void __launch_bounds__(NT, MINB) k_cluster_rings(
     const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta,
     const int* __restrict__ cropCnt, const long long* __restrict__ scan_off,
@@ -845,10 +871,11 @@ __global__ void __launch_bounds__(NT, MINB) k_cluster_rings(
     float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
     float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
     DevCounters* __restrict__ ctr, const int* __restrict__ scanList, const int* __restrict__ nList,
-    int* __restrict__ ovfList, int* __restrict__ ovfCount) {
+    int* __restrict__ ovfList, int* __restrict__ ovfCount, unsigned char* __restrict__ slabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
-  cluster_sm_carve<CAP, NT>(smem_raw, S);
+  if (GLOBAL) cluster_carve_global<CAP, NT>(slabs + (size_t)blockIdx.x * cluster_slab_bytes(CAP), smem_raw, S);
+  else cluster_sm_carve<CAP, NT>(smem_raw, S);
   if (!scanList) {
     cluster_rings_scan<CAP, NT>(S, blockIdx.x, crop, cropMeta, cropCnt, scan_off, chunk_off, P, single_ring, kfPool, kfCap,
                             kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfList, ovfCount);
@@ -871,7 +898,7 @@ __device__ void merge_keypoints_scan(
     ClusterSm& S, const int s, const float4* __restrict__ kfPool, const int* __restrict__ kfBase,
     const int* __restrict__ kfCnt, const DevParams& P, float4* __restrict__ kpPool, int kpCap,
     int* __restrict__ kpBase, int* __restrict__ kpCnt, DevCounters* __restrict__ ctr,
-    int* __restrict__ ovfList) {
+    int* __restrict__ ovfList, int* __restrict__ ovfCount) {
   const int tid = threadIdx.x;
   int* sc = S.misc + MAXCHUNK + 1;
   int* pre = S.misc;  // 17 prefix entries of the pieces
@@ -886,7 +913,7 @@ __device__ void merge_keypoints_scan(
   if (Kf == 0) return;
   if (Kf > CAP) {
     if (tid == 0) {
-      if (ovfList) ovfList[atomicAdd(&ctr->ovf_merge, 1)] = s;  // the large instantiation takes it
+      if (ovfList) ovfList[atomicAdd(ovfCount, 1)] = s;  // the next larger instantiation takes it
       else atomicOr(&ctr->err, ERR_MERGE_CAP);
     }
     return;
@@ -937,33 +964,38 @@ __device__ void merge_keypoints_scan(
   }
 }
 
-template <int CAP, int NT, int MINB>
+template <int CAP, int NT, int MINB, bool GLOBAL>
 __global__ void __launch_bounds__(NT, MINB) k_merge_keypoints(
     const float4* __restrict__ kfPool, const int* __restrict__ kfBase, const int* __restrict__ kfCnt,
     DevParams P, float4* __restrict__ kpPool, int kpCap, int* __restrict__ kpBase,
     int* __restrict__ kpCnt, DevCounters* __restrict__ ctr, const int* __restrict__ scanList,
-    const int* __restrict__ nList, int* __restrict__ ovfList) {
+    const int* __restrict__ nList, int* __restrict__ ovfList, int* __restrict__ ovfCount,
+    unsigned char* __restrict__ slabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
-  cluster_sm_carve<CAP, NT>(smem_raw, S);
+  if (GLOBAL) cluster_carve_global<CAP, NT>(slabs + (size_t)blockIdx.x * cluster_slab_bytes(CAP), smem_raw, S);
+  else cluster_sm_carve<CAP, NT>(smem_raw, S);
   if (!scanList) {
-    merge_keypoints_scan<CAP, NT>(S, blockIdx.x, kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, ovfList);
+    merge_keypoints_scan<CAP, NT>(S, blockIdx.x, kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, ovfList, ovfCount);
   } else {
     const int n = *nList;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
       __syncthreads();
-      merge_keypoints_scan<CAP, NT>(S, scanList[i], kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, nullptr);
+      merge_keypoints_scan<CAP, NT>(S, scanList[i], kfPool, kfBase, kfCnt, P, kpPool, kpCap, kpBase, kpCnt, ctr, ovfList, ovfCount);
     }
   }
 }
 
 // Stage kernel: plain EuclideanClusterExtraction of n points (one block), CSR result.
+template <bool GLOBAL>
 __global__ void __launch_bounds__(NT2, 1) k_extract_clusters_stage(
     const float4* __restrict__ pts, int n, float tol_f, float r2f, int minSz, int maxSz,
-    int* __restrict__ offsets, int capClusters, int* __restrict__ indices, int* __restrict__ nOut) {
+    int* __restrict__ offsets, int capClusters, int* __restrict__ indices, int* __restrict__ nOut,
+    unsigned char* __restrict__ slabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClusterSm S;
-  cluster_sm_carve<ECAP_L, NT2>(smem_raw, S);
+  if (GLOBAL) cluster_carve_global<ECAP_G, NT2>(slabs, smem_raw, S);
+  else cluster_sm_carve<ECAP_L, NT2>(smem_raw, S);
   const int tid = threadIdx.x;
   for (int i = tid; i < n; i += NT2) {
     const float4 q = pts[i];

@@ -177,3 +177,25 @@ def test_elevation_fast_path_rounds_like_the_double_evaluation(ob, node):
     if len(diff):
         assert np.all(np.abs(g[diff, 3] - o[diff, 3]) <= np.spacing(np.abs(o[diff, 3])))
     assert bits_equal(g[:, :3], pts[:, :3])
+
+
+def test_oversized_rings_take_the_global_memory_path(ob, node):
+    """A ring with more cropped returns than any shared-memory instantiation holds (6144) is not an
+    error: the clustering falls through to the instantiation whose arrays live in global memory."""
+    rng = np.random.default_rng(5)
+    P = ob.node_default()
+    # ~9000 returns in ONE ring (elevation -1 deg): 900 small clumps of 10 points on a grid in the crop box
+    pts = []
+    for c in range(900):
+        cx, cy = 2.0 + 1.6 * (c % 45), -28.0 + 2.8 * (c // 45)
+        for k in range(10):
+            pts.append((cx + 0.02 * k + 0.003 * rng.normal(), cy + 0.003 * rng.normal(), 0.1 * rng.normal(), -1.0))
+    pts = np.array(pts, np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    kp_o, kc_o, kf_o = ob.estimate_keypoints(P, pts, mode=1)
+    kp_g, kc_g = node.estimateKeypoints(pts)
+    assert len(kf_o) > 500
+    assert bits_equal(kp_g, kp_o) and bits_equal(kc_g, kc_o)
+    co = ob.extract_clusters(pts, 0.65, 5, 50, mode=1)
+    cg = node.extractClusters(pts, 0.65, 5, 50)
+    assert len(co) == len(cg) and all(np.array_equal(a, b) for a, b in zip(co, cg))
