@@ -356,10 +356,8 @@ int set_kernel_attrs(fe_ctx* ctx) {
                           (int)desc_smem_bytes(DCAP_M, 512)));
   CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_L, DCAP_M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)desc_smem_bytes(DCAP_L, 512)));
-  CK(cudaFuncSetAttribute(k_surface_grid_smem<unsigned short, SCAP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)surf_smem_bytes(SCAP16, 2)));
-  CK(cudaFuncSetAttribute(k_surface_grid_smem<unsigned, SCAP32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)surf_smem_bytes(SCAP32, 4)));
+  CK(cudaFuncSetAttribute(k_surface_grid_cells, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)surf_cells_smem_bytes(SURF_MAX_CELLS)));
   return FE_OK;
 }
 
@@ -374,18 +372,20 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
   ctx->launches += 3;
 }
 
-// K4a: shared-memory sort for scans that fit, global-memory sort for the deferred rest.
+// K4a: counting sort by cell in shared memory for scans that fit (<= 65,535 surface points, grid <=
+// SURF_MAX_CELLS cells), radix sort through global memory for the deferred rest.
 void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
-  const int keybits = P.sg_bx + bits_for_host(P.sg_ny - 1);
-  if (keybits <= 16)
-    k_surface_grid_smem<unsigned short, SCAP16><<<nscans, NT2, surf_smem_bytes(SCAP16, 2), s.stream>>>(
+  const int ncells = P.sg_nx * P.sg_ny;
+  if (ncells <= SURF_MAX_CELLS) {
+    k_surface_grid_cells<<<nscans, NT2, surf_cells_smem_bytes(ncells), s.stream>>>(
         s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf);
-  else
-    k_surface_grid_smem<unsigned, SCAP32><<<nscans, NT2, surf_smem_bytes(SCAP32, 4), s.stream>>>(
-        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf);
-  k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB,
-                                                                 s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN,
-                                                                 s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf);
+    k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
+                                                                   s.d_keyB, s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey,
+                                                                   s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf);
+  } else {
+    k_surface_grid<<<nscans, NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA,
+                                                 s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, nullptr, nullptr);
+  }
   ctx->launches += 2;
 }
 

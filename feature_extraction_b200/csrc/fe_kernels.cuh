@@ -1,18 +1,21 @@
 // fe_kernels.cuh — the sm_100a kernels of the per-scan keypoint pipeline.
 //
 //   K1  k_level_crop_ring     getElevationAngles + rotateCloud + filterCloud + ring bucketing
-//                             (reference src:147-183, 200-202), fused, one pass over the points
+//                             (reference src:147-183, 200-202), fused, one pass over the points;
+//                             decodes PointCloud2-style records in place when asked to
 //   K2  k_cluster_rings       per-ring EuclideanClusterExtraction + getCylinderSegments gating
-//                             (src:261-327): uniform grid (cell = tolerance) built by a block
-//                             radix sort of cell keys in shared memory, atomic union-find over
-//                             the neighbour cells, segmented per-cluster reductions
-//   K3  k_merge_keypoints     cross-ring merge of ring centroids (src:205-257)
-//   K4a k_surface_grid        2-D cell sort of the descriptor search surface (cell >= R/5)
+//                             (src:261-327): uniform grid (cell = 0.55 x tolerance) built by a block
+//                             radix sort of cell keys in shared memory, atomic union-find over the
+//                             neighbour cells, segmented per-cluster reductions
+//   K3  k_merge_keypoints     cross-ring merge of ring centroids (src:205-257), same machinery
+//   K4a k_surface_grid[_smem] 2-D cell sort of the descriptor search surface (cell >= R/5)
 //   K4b k_desc_mark           which surface points are inside some keypoint's sphere
 //   K4c k_density             3DSC local point density, once per marked point
-//   K4d k_desc_hist           1980-bin shape context per keypoint, shared-memory histogram
+//   K4d k_desc_hist           1980-bin shape context per keypoint, contributions summed in PCL's order
 //
 // Batched over scans: every kernel addresses scan s through CSR offsets; blocks never cross scans.
+// Per-scan kernels come as chains of instantiations (fast -> large shared memory -> global-memory
+// slab): a block that finds its scan too big defers it to a device list for the next one.
 #pragma once
 #include <math.h>
 #include "fe_device.cuh"
@@ -31,7 +34,6 @@ constexpr int NTM = 64;
 constexpr int NTL = 1024;      // threads of the large K2 instantiation
 constexpr int ECAP_G = 65535;   // last resort: per-entry arrays in a global-memory slab (16-bit entry indices)
 constexpr int NGLOBAL = 32;     // blocks (and slabs) of the global-memory instantiations
-constexpr int ECAP_MD = 2944;   // K2 medium instantiation (512 threads, 2 blocks / SM) for denser scans
 constexpr int ECAP_L = 6144;    // the large instantiations (1 block / SM) for scans the fast ones defer
 
 // error bits reported through DevCounters::err
@@ -1191,73 +1193,101 @@ __global__ void __launch_bounds__(NT2, 2) k_surface_grid(
   }
 }
 
-// Shared-memory K4a: the whole (key, index) sort of one scan stays in shared memory (16-bit keys
-// when the grid has <= 65536 cells), so HBM/L2 only sees the points once for the keys, once for the
-// gather, and the sorted output.  Scans with more than SCAP surface points are deferred.
-template <typename KeyT, int SCAP>
-__global__ void __launch_bounds__(NT2, 2) k_surface_grid_smem(
+// Shared-memory K4a: a counting sort by grid cell.  Nothing downstream depends on the order of the
+// points inside a cell (K4b marks, K4c counts, K4d orders its records itself), so the sort is:
+// count the points of every cell (16-bit counters, two per shared-memory word), exclusive-scan the
+// cells (their starts; the row starts fall out of it), then scatter every point to the next free
+// slot of its cell.  Two coalesced sweeps over the scan's surface pieces, no key/value ping-pong.
+// Scans with more than 65,535 surface points (16-bit counters) are deferred to the radix kernel.
+constexpr int SURF_MAX_CELLS = 57344;  // 112 KB of counters: 2 blocks / SM at the upper end
+constexpr size_t surf_cells_smem_bytes(int ncells) { return (size_t)((ncells + 1) / 2) * 4 + 64; }
+
+__global__ void __launch_bounds__(NT2) k_surface_grid_cells(
     const float4* __restrict__ surf, const int* __restrict__ surfCnt,
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
     float4* __restrict__ sorted, unsigned* __restrict__ sortedKey, int* __restrict__ rowStart,
     int* __restrict__ surfN, DevCounters* __restrict__ ctr, int* __restrict__ ovfList) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  KeyT* kA = (KeyT*)smem_raw;
-  KeyT* kB = kA + SCAP;
-  unsigned short* vA = (unsigned short*)(kB + SCAP);
-  unsigned short* vB = vA + SCAP;
-  unsigned short* wc = vB + SCAP;                       // (NT2/32)*257
-  unsigned* rbase = (unsigned*)(wc + (NT2 / 32) * 257);  // 288; (NT2/32)*257 is even: 4-byte aligned
-  int* pre = (int*)(rbase + 288);                       // MAXCHUNK+1
-  int* sc = pre + MAXCHUNK + 1;                         // 40
-  const int s = blockIdx.x, tid = threadIdx.x;
+  unsigned* cells = (unsigned*)smem_raw;  // packed pairs of 16-bit counters / cursors
+  __shared__ int sc[40];
+  __shared__ int s_n;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int NW = NT2 / 32;
   const long long base = scan_off[s];
-  const int nch = chunk_off[s + 1] - chunk_off[s];
-  int* rs = rowStart + (long long)s * (P.sg_ny + 1);
-  if (nch > MAXCHUNK) { if (tid == 0) { atomicOr(&ctr->err, ERR_CHUNKS); surfN[s] = 0; } return; }
-  const int n = chunk_prefix<NT2>(surfCnt + chunk_off[s], nch, pre, sc);
-  if (n > SCAP) {
+  const int c0 = chunk_off[s];
+  const int nch = chunk_off[s + 1] - c0;
+  const int nx = P.sg_nx, ny = P.sg_ny, ncells = nx * ny, nwords = (ncells + 1) / 2;
+  int* rs = rowStart + (long long)s * (ny + 1);
+  // total surface points of the scan
+  {
+    int v = 0;
+    for (int c = tid; c < nch; c += NT2) v += surfCnt[c0 + c];
+    int tot;
+    block_excl_scan<NT2>(v, &tot, sc);
+    if (tid == 0) s_n = tot;
+  }
+  for (int i = tid; i < nwords; i += NT2) cells[i] = 0u;
+  __syncthreads();
+  const int n = s_n;
+  if (n > 65535) {
     if (tid == 0) ovfList[atomicAdd(&ctr->ovf_surf, 1)] = s;
     return;
   }
   if (tid == 0) surfN[s] = n;
   if (n == 0) {
-    for (int r = tid; r <= P.sg_ny; r += NT2) rs[r] = 0;
+    for (int r = tid; r <= ny; r += NT2) rs[r] = 0;
     return;
   }
-  for (int i = tid; i < n; i += NT2) {
-    const float4 q = surf[piece_pos(pre, nch, i, base)];
-    const int cx = surf_cell(q.x, P.sx0, P.sg_inv, P.sg_nx), cy = surf_cell(q.y, P.sy0, P.sg_inv, P.sg_ny);
-    kA[i] = (KeyT)(((unsigned)cy << P.sg_bx) | (unsigned)cx);
-    vA[i] = (unsigned short)i;
-  }
-  const int keybits = P.sg_bx + bits_for(P.sg_ny - 1);
-  KeyT *kS = kA, *kT = kB;
-  unsigned short *vS = vA, *vT = vB;
-  for (int shift = 0; shift < keybits; shift += 8) {
-    KeyT* ki = kS; KeyT* ko = kT; unsigned short* vi = vS; unsigned short* vo = vT;
-    block_radix_pass<NT2, unsigned short>(
-        n, [=](int i) { return ((unsigned)ki[i] >> shift) & 255u; },
-        [=](int i, int pos) { ko[pos] = ki[i]; vo[pos] = vi[i]; }, wc, rbase);
-    kS = ko; kT = ki; vS = vo; vT = vi;
+  // (1) count: warp w sweeps chunks w, w+NW, ... (their survivors are contiguous)
+  for (int c = w; c < nch; c += NW) {
+    const int cnt = surfCnt[c0 + c];
+    const float4* src = surf + base + (long long)c * CH;
+    for (int j = lane; j < cnt; j += 32) {
+      const float4 q = src[j];
+      const int cell = surf_cell(q.y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q.x, P.sx0, P.sg_inv, nx);
+      atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
+    }
   }
   __syncthreads();
+  // (2) exclusive scan over the cells in key order; every thread owns a run of whole words
+  {
+    const int per = (nwords + NT2 - 1) / NT2;
+    const int wb = min(tid * per, nwords), we = min(wb + per, nwords);
+    int sum = 0;
+    for (int i = wb; i < we; i++) { const unsigned v = cells[i]; sum += (int)(v & 0xFFFFu) + (int)(v >> 16); }
+    int tot;
+    int run = block_excl_scan<NT2>(sum, &tot, sc);
+    for (int i = wb; i < we; i++) {
+      const unsigned v = cells[i];
+      const int lo = (int)(v & 0xFFFFu), hi = (int)(v >> 16);
+      cells[i] = (unsigned)run | ((unsigned)(run + lo) << 16);  // starts of the two cells
+      run += lo + hi;
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r <= ny; r += NT2) {
+    int v = n;
+    if (r < ny) { const int cell = r * nx; const unsigned wv = cells[cell >> 1]; v = (cell & 1) ? (int)(wv >> 16) : (int)(wv & 0xFFFFu); }
+    rs[r] = v;
+  }
+  __syncthreads();
+  // (3) scatter: the start of a cell doubles as its cursor (it ends at the cell's end <= n <= 65535,
+  //     so a 16-bit half never carries into its neighbour)
   float4* so = sorted + base;
   unsigned* sk = sortedKey + base;
-  for (int i = tid; i < n; i += NT2) {
-    const unsigned k = (unsigned)kS[i];
-    so[i] = surf[piece_pos(pre, nch, (int)vS[i], base)];
-    sk[i] = k;
-    const int r = (int)(k >> P.sg_bx);
-    const int rp = (i == 0) ? -1 : (int)((unsigned)kS[i - 1] >> P.sg_bx);
-    for (int rr = rp + 1; rr <= r; rr++) rs[rr] = i;
-    if (i == n - 1) for (int rr = r + 1; rr <= P.sg_ny; rr++) rs[rr] = n;
+  for (int c = w; c < nch; c += NW) {
+    const int cnt = surfCnt[c0 + c];
+    const float4* src = surf + base + (long long)c * CH;
+    for (int j = lane; j < cnt; j += 32) {
+      const float4 q = src[j];
+      const int cx = surf_cell(q.x, P.sx0, P.sg_inv, nx), cy = surf_cell(q.y, P.sy0, P.sg_inv, ny);
+      const int cell = cy * nx + cx;
+      const unsigned old = atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
+      const int pos = (cell & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu);
+      so[pos] = q;
+      sk[pos] = ((unsigned)cy << P.sg_bx) | (unsigned)cx;
+    }
   }
-}
-
-constexpr int SCAP16 = 12288;  // surface points per scan, 16-bit keys (2 blocks / SM)
-constexpr int SCAP32 = 8192;   // 32-bit keys
-constexpr size_t surf_smem_bytes(int scap, int keybytes) {
-  return (size_t)scap * (2 * keybytes + 4) + ((NT2 / 32) * 257) * 2 + 288 * 4 + (MAXCHUNK + 1 + 40) * 4 + 16;
 }
 
 // span of sorted positions of row r whose cell x is in [cx0, cx1]

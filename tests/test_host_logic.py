@@ -134,3 +134,24 @@ def test_imu_to_roll_pitch_matches_oracle_and_known_cases(ob):
     a = np.deg2rad(30.0)
     r, p = imu_to_roll_pitch([0, np.sin(a / 2), 0, np.cos(a / 2)])
     assert abs(p - a) < 1e-12 and abs(r + np.pi) < 1e-12
+
+
+def test_null_and_invalid_arguments_are_status_codes_not_crashes():
+    """No exception or crash crosses the C-ABI: bad arguments come back as FE_ERR_INVALID."""
+    from feature_extraction_b200 import _native as N
+    L = N.lib()
+    res = N.BatchResult()
+    assert L.fe_process_batch(None, None, None, None, 0, C.byref(res)) == N.FE_ERR_INVALID
+    assert L.fe_process_batch_device(None, None, None, None, 0, C.byref(res)) == N.FE_ERR_INVALID
+    assert L.fe_create(0, None, None, None) == N.FE_ERR_INVALID
+    assert L.fe_set_params(None, None) == N.FE_ERR_INVALID
+    assert L.fe_get_elevation_angles(None, None, 0) == N.FE_ERR_INVALID
+    assert L.fe_filter_cloud(None, None, 0, None, 0, None) == N.FE_ERR_INVALID
+    assert L.fe_estimate_descriptors(None, None, 0, None, 0, None) == N.FE_ERR_INVALID
+    assert L.fe_rotation_matrix(0.0, 0.0, None) == N.FE_ERR_INVALID
+    assert L.fe_pack_point_descriptors(None, None, 1, None) == N.FE_ERR_INVALID
+    assert L.fe_pack_point_descriptors(None, None, 0, None) == N.FE_OK
+    L.fe_destroy(None)  # no-op
+    assert L.fe_last_error(None) == b"null context"
+    lay = N.PointLayout(8, 0, 4, 8)
+    assert L.fe_process_batch_layout(None, None, C.byref(lay), None, None, 0, C.byref(res)) == N.FE_ERR_INVALID
