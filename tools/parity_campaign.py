@@ -1,0 +1,34 @@
+"""Large GPU-vs-oracle parity sweep (run under gpurun); writes a markdown summary to gpurun_out/."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from oracle import oracle_binding as ob
+from feature_extraction_b200 import FeatureExtractionNode, synth
+from util import to_fe_params
+
+rows = []
+for cfg, nsc, base in ((1, 400, 5000), (2, 4000, 50000), (3, 160, 7000), (4, 240, 9000)):
+    P = ob.launch_playback() if cfg == 1 else ob.node_default()
+    if cfg == 4: P.descriptor_radius = 5.0
+    pts, offs, rp = synth.generate(cfg, nsc, scan_index_base=base)
+    nd = FeatureExtractionNode(to_fe_params(P), max_points=int(offs[-1]) + 4096, max_scans=nsc, max_keypoints=max(4096, nsc * 64))
+    t = time.time(); ko, kp, d = nd.processBatch(pts, offs, rp); tg = time.time() - t
+    t = time.time(); ko_o, kp_o, d_o, m_o = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=len(os.sched_getaffinity(0)), want_margin=True); tc = time.time() - t
+    same_off = bool(np.array_equal(ko, ko_o))
+    kp_bits = bool(same_off and np.array_equal(kp.view(np.uint32), kp_o.view(np.uint32)))
+    row_exact = (d.view(np.uint32) == d_o.view(np.uint32)).all(axis=1) if same_off else np.zeros(0, bool)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = np.abs(d.astype(np.float64) - d_o) / np.maximum(np.abs(d_o), 1e-300)
+    rel = np.where((d == d_o) | (np.isnan(d) & np.isnan(d_o)), 0, rel).max(axis=1) if same_off else np.zeros(0)
+    inexact = np.flatnonzero(~row_exact)
+    rows.append((cfg, nsc, int(offs[-1]), len(kp_o), same_off, kp_bits, int(row_exact.sum()), len(inexact),
+                 float(rel.max()) if len(rel) else 0.0, int((rel > 1e-5).sum()), float(m_o[inexact].min()) if len(inexact) else float("nan"), tg, tc))
+    nd.close()
+out = ["# Parity campaign (GPU C-ABI vs CPU oracle, KD-tree mode), round 1", "",
+       "| config | scans | points | keypoints | counts equal | keypoints bit-equal | descriptor rows bit-equal | rows not bit-equal | max rel err | rows > 1e-5 | min edge margin of inexact rows | GPU s (pageable host) | oracle s (all cores) |",
+       "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+for r in rows:
+    out.append("| %d | %d | %d | %d | %s | %s | %d | %d | %.3g | %d | %.3g | %.3f | %.2f |" % r)
+open(os.path.join(ROOT, "gpurun_out", "parity_campaign.md"), "w").write("\n".join(out) + "\n")
+print("\n".join(out))
