@@ -1238,11 +1238,14 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
     for (int r = tid; r <= ny; r += NT2) rs[r] = 0;
     return;
   }
-  // (1) count: warp w sweeps chunks w, w+NW, ... (their survivors are contiguous)
-  for (int c = w; c < nch; c += NW) {
+  // (1) count: the survivors of a chunk are contiguous; every chunk is cut into 8 slices and the
+  //     slices are dealt to the warps (a scan has fewer chunks than the block has warps)
+  for (int it = w; it < nch * 8; it += NW) {
+    const int c = it >> 3, sl = it & 7;
     const int cnt = surfCnt[c0 + c];
+    const int j1 = (cnt * (sl + 1)) >> 3;
     const float4* src = surf + base + (long long)c * CH;
-    for (int j = lane; j < cnt; j += 32) {
+    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 32) {
       const float4 q = src[j];
       const int cell = surf_cell(q.y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q.x, P.sx0, P.sg_inv, nx);
       atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
@@ -1275,10 +1278,12 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   //     so a 16-bit half never carries into its neighbour)
   float4* so = sorted + base;
   unsigned* sk = sortedKey + base;
-  for (int c = w; c < nch; c += NW) {
+  for (int it = w; it < nch * 8; it += NW) {
+    const int c = it >> 3, sl = it & 7;
     const int cnt = surfCnt[c0 + c];
+    const int j1 = (cnt * (sl + 1)) >> 3;
     const float4* src = surf + base + (long long)c * CH;
-    for (int j = lane; j < cnt; j += 32) {
+    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 32) {
       const float4 q = src[j];
       const int cx = surf_cell(q.x, P.sx0, P.sg_inv, nx), cy = surf_cell(q.y, P.sy0, P.sg_inv, ny);
       const int cell = cy * nx + cx;
