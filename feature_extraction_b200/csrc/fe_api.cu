@@ -33,6 +33,9 @@ struct Slot {
   int *d_kfBase = nullptr, *d_kfCnt = nullptr, *d_kcBase = nullptr, *d_kcCnt = nullptr;
   int *d_kpBase = nullptr, *d_kpCnt = nullptr, *d_kpOff = nullptr, *d_kpScan = nullptr, *d_kpNbr = nullptr;
   int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
+  unsigned short* d_cellTab = nullptr;
+  int* d_tabOk = nullptr;
+  int64_t capCellTab = 0;
   int *d_ovfRings = nullptr, *d_ovfRings2 = nullptr, *d_ovfMerge = nullptr, *d_ovfMerge2 = nullptr, *d_ovfSurf = nullptr;
   unsigned char* d_slabs = nullptr;
   int64_t capRowStart = 0;
@@ -217,7 +220,7 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
   for (void* p : hv) if (p) cudaFreeHost(p);
@@ -258,7 +261,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_kcBase, ns * 16)); CK(dalloc(&s.d_kcCnt, ns * 16));
   CK(dalloc(&s.d_kpBase, ns)); CK(dalloc(&s.d_kpCnt, ns)); CK(dalloc(&s.d_kpOff, ns + 1));
   CK(dalloc(&s.d_kpScan, (size_t)s.capKp)); CK(dalloc(&s.d_kpNbr, (size_t)s.capKp));
-  CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1));
+  CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1)); CK(dalloc(&s.d_tabOk, ns));
   CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfRings2, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfMerge2, ns));
   CK(dalloc(&s.d_ovfSurf, ns));
   CK(dalloc(&s.d_slabs, (size_t)NGLOBAL * cluster_slab_bytes(ECAP_G)));
@@ -328,7 +331,27 @@ int ensure_rowstart(fe_ctx* ctx, Slot& s, int nscans) {
     CK(dalloc(&s.d_rowStart, (size_t)need));
     s.capRowStart = need;
   }
+  const int64_t ncells = (int64_t)ctx->dp.sg_nx * ctx->dp.sg_ny;
+  if (ncells <= SURF_MAX_CELLS) {
+    const int64_t needT = (int64_t)std::max(nscans, s.capScans) * (ncells + 1);
+    if (needT > s.capCellTab) {
+      if (s.d_cellTab) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.d_cellTab)); s.d_cellTab = nullptr; }
+      CK(dalloc(&s.d_cellTab, (size_t)needT));
+      s.capCellTab = needT;
+    }
+  }
   return FE_OK;
+}
+
+SurfIndex surf_index(const fe_ctx* ctx, const Slot& s) {
+  const int64_t ncells = (int64_t)ctx->dp.sg_nx * ctx->dp.sg_ny;
+  SurfIndex X;
+  X.sortedKey = s.d_sortedKey;
+  X.rowStart = s.d_rowStart;
+  X.cellTab = (ncells <= SURF_MAX_CELLS) ? s.d_cellTab : nullptr;
+  X.tabOk = s.d_tabOk;
+  X.ncells1 = (int)(ncells + 1);
+  return X;
 }
 
 int ensure_kc(fe_ctx* ctx, Slot& s) {
@@ -363,7 +386,7 @@ int set_kernel_attrs(fe_ctx* ctx) {
 
 // K4d: three instantiations split the keypoints by neighbour count (smaller footprint = more blocks / SM)
 void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp) {
-#define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P, \
+#define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, \
                      s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_desc, s.d_ctr
   k_desc_hist<256, DCAP, 0, false><<<gridKp, 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
   k_desc_hist<512, DCAP_M, DCAP, false><<<std::min(gridKp, 148 * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
@@ -378,13 +401,16 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
   const int ncells = P.sg_nx * P.sg_ny;
   if (ncells <= SURF_MAX_CELLS) {
     k_surface_grid_cells<<<nscans, NT2, surf_cells_smem_bytes(ncells), s.stream>>>(
-        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf);
+        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf,
+        s.d_cellTab, s.d_tabOk);
     k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
                                                                    s.d_keyB, s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey,
-                                                                   s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf);
+                                                                   s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf,
+                                                                   s.d_tabOk);
   } else {
     k_surface_grid<<<nscans, NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA,
-                                                 s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, nullptr, nullptr);
+                                                 s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, nullptr, nullptr,
+                                                 s.d_tabOk);
   }
   ctx->launches += 2;
 }
@@ -460,13 +486,13 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     launch_surface_grid(ctx, s, nscans, P);
     mark(ctx, s, "K4a surface grid");
     const int gridKp = 148 * 8;
-    k_desc_mark<<<gridKp, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, s.d_sortedKey, s.d_rowStart,
-                                              s.d_scan_off, P, s.d_rho, s.d_kpNbr);
+    k_desc_mark<<<gridKp, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P,
+                                              s.d_rho, s.d_kpNbr);
     ctx->launches++;
     mark(ctx, s, "K4b mark neighbours");
     if (npts > 0) {
       const int gridD = (int)std::min<int64_t>((npts + 255) / 256, 148 * 64);
-      k_density<<<gridD, 256, 0, s.stream>>>(s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P, (long long)npts, s.d_rho);
+      k_density<<<gridD, 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, (long long)npts, s.d_rho);
       ctx->launches++;
     }
     mark(ctx, s, "K4c density");
@@ -1127,10 +1153,10 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
       cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(int), q) != cudaSuccess)
     return restore(fail(ctx, FE_ERR_CUDA, "staging of the descriptor inputs failed"));
   launch_surface_grid(ctx, s, 1, P);
-  k_desc_mark<<<148 * 4, 256, 0, q>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, 1, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P,
-                                      s.d_rho, s.d_kpNbr);
+  k_desc_mark<<<148 * 4, 256, 0, q>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, 1, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, s.d_rho,
+                                      s.d_kpNbr);
   if (n > 0) {
-    k_density<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 64), 256, 0, q>>>(s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_scan_off, P,
+    k_density<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 64), 256, 0, q>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P,
                                                                                (long long)n, s.d_rho);
     ctx->launches++;
   }

@@ -1178,15 +1178,17 @@ __global__ void __launch_bounds__(NT2, 2) k_surface_grid(
     unsigned* __restrict__ keyA, unsigned* __restrict__ keyB, unsigned* __restrict__ valA,
     unsigned* __restrict__ valB, float4* __restrict__ sorted, unsigned* __restrict__ sortedKey,
     int* __restrict__ rowStart, int* __restrict__ surfN, DevCounters* __restrict__ ctr,
-    const int* __restrict__ scanList, const int* __restrict__ nList) {
+    const int* __restrict__ scanList, const int* __restrict__ nList, int* __restrict__ tabOk) {
   __shared__ SurfGlobalSm M;
   if (!scanList) {
+    if (threadIdx.x == 0) tabOk[blockIdx.x] = 0;
     surface_grid_scan_global(M, blockIdx.x, surf, surfCnt, scan_off, chunk_off, P, keyA, keyB, valA, valB, sorted, sortedKey,
                              rowStart, surfN, ctr);
   } else {
     const int n = *nList;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
       __syncthreads();
+      if (threadIdx.x == 0) tabOk[scanList[i]] = 0;
       surface_grid_scan_global(M, scanList[i], surf, surfCnt, scan_off, chunk_off, P, keyA, keyB, valA, valB, sorted,
                                sortedKey, rowStart, surfN, ctr);
     }
@@ -1206,7 +1208,8 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
     const float4* __restrict__ surf, const int* __restrict__ surfCnt,
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
     float4* __restrict__ sorted, unsigned* __restrict__ sortedKey, int* __restrict__ rowStart,
-    int* __restrict__ surfN, DevCounters* __restrict__ ctr, int* __restrict__ ovfList) {
+    int* __restrict__ surfN, DevCounters* __restrict__ ctr, int* __restrict__ ovfList,
+    unsigned short* __restrict__ cellTab, int* __restrict__ tabOk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned* cells = (unsigned*)smem_raw;  // packed pairs of 16-bit counters / cursors
   __shared__ int sc[40];
@@ -1230,12 +1233,14 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   __syncthreads();
   const int n = s_n;
   if (n > 65535) {
-    if (tid == 0) ovfList[atomicAdd(&ctr->ovf_surf, 1)] = s;
+    if (tid == 0) { ovfList[atomicAdd(&ctr->ovf_surf, 1)] = s; tabOk[s] = 0; }
     return;
   }
-  if (tid == 0) surfN[s] = n;
+  if (tid == 0) { surfN[s] = n; tabOk[s] = 1; }
+  unsigned short* tab = cellTab + (long long)s * (ncells + 1);
   if (n == 0) {
     for (int r = tid; r <= ny; r += NT2) rs[r] = 0;
+    for (int i = tid; i <= ncells; i += NT2) tab[i] = 0;
     return;
   }
   // (1) count: the survivors of a chunk are contiguous; every chunk is cut into 8 slices and the
@@ -1273,6 +1278,13 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
     if (r < ny) { const int cell = r * nx; const unsigned wv = cells[cell >> 1]; v = (cell & 1) ? (int)(wv >> 16) : (int)(wv & 0xFFFFu); }
     rs[r] = v;
   }
+  // the table of cell starts for K4b-d (32-bit stores of two cells; the table is 4-byte aligned per scan
+  // only when ncells+1 is even, so the tail and odd layouts go element-wise)
+  for (int i = tid; i < ncells; i += NT2) {
+    const unsigned wv = cells[i >> 1];
+    tab[i] = (unsigned short)((i & 1) ? (wv >> 16) : (wv & 0xFFFFu));
+  }
+  if (tid == 0) tab[ncells] = (unsigned short)n;
   __syncthreads();
   // (3) scatter: the start of a cell doubles as its cursor (it ends at the cell's end <= n <= 65535,
   //     so a 16-bit half never carries into its neighbour)
@@ -1295,9 +1307,26 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   }
 }
 
+// How K4b-d find the sorted positions of a cell range: through the per-scan table of cell starts that
+// the counting-sort K4a publishes (two loads), or — for scans that went through the radix kernel —
+// by binary search in the sorted keys inside the row.
+struct SurfIndex {
+  const unsigned* sortedKey;      // keys of the sorted points (CSR by scan)
+  const int* rowStart;            // [scan][ny+1]
+  const unsigned short* cellTab;  // [scan][ncells+1] first slot of every cell (last = n), may be null
+  const int* tabOk;               // [scan] 1: the scan has a cell table
+  int ncells1;                    // ncells + 1
+};
+
 // span of sorted positions of row r whose cell x is in [cx0, cx1]
 __device__ __forceinline__ void row_span(const unsigned* __restrict__ sk, const int* __restrict__ rs,
-                                         int r, int cx0, int cx1, int bx, int& b, int& e) {
+                                         const unsigned short* __restrict__ ct, int nx, int r, int cx0, int cx1,
+                                         int bx, int& b, int& e) {
+  if (ct) {
+    b = (int)ct[r * nx + cx0];
+    e = (int)ct[r * nx + cx1 + 1];
+    return;
+  }
   const int rb = rs[r], re = rs[r + 1];
   const unsigned klo = ((unsigned)r << bx) | (unsigned)cx0, khi = ((unsigned)r << bx) | (unsigned)cx1;
   int lo = rb, hi = re;
@@ -1315,8 +1344,7 @@ __device__ __forceinline__ void row_span(const unsigned* __restrict__ sk, const 
 // ============================================================================================
 __global__ void __launch_bounds__(256) k_desc_mark(
     const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
-    int n_scans, const float4* __restrict__ sorted, const unsigned* __restrict__ sortedKey,
-    const int* __restrict__ rowStart, const long long* __restrict__ scan_off, DevParams P,
+    int n_scans, const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P,
     int* __restrict__ rho, int* __restrict__ kpNbr) {
   __shared__ int s_cnt;
   const int total = kpOff[n_scans];
@@ -1330,13 +1358,14 @@ __global__ void __launch_bounds__(256) k_desc_mark(
     if (finite3(o.x, o.y, o.z)) {
       const long long base = scan_off[s];
       const float4* so = sorted + base;
-      const unsigned* sk = sortedKey + base;
-      const int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+      const unsigned* sk = X.sortedKey + base;
+      const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+      const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
       const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
       const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
       for (int r = cy0 + w; r <= cy1; r += 8) {
         int b, e;
-        row_span(sk, rs, r, cx0, cx1, P.sg_bx, b, e);
+        row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
         for (int i = b + lane; i < e; i += 32) {
           const float4 q = so[i];
           const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
@@ -1358,8 +1387,7 @@ __global__ void __launch_bounds__(256) k_desc_mark(
 // marked surface point instead of once per (keypoint, neighbour) as PCL does.
 // ============================================================================================
 __global__ void __launch_bounds__(256) k_density(
-    const float4* __restrict__ sorted, const unsigned* __restrict__ sortedKey,
-    const int* __restrict__ rowStart, const long long* __restrict__ scan_off, DevParams P,
+    const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P,
     long long total, int* __restrict__ rho) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1368,19 +1396,17 @@ __global__ void __launch_bounds__(256) k_density(
     const int s = -v - 1;
     const long long base = scan_off[s];
     const float4* so = sorted + base;
-    const unsigned* sk = sortedKey + base;
-    const int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+    const unsigned* sk = X.sortedKey + base;
+    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
     const float4 p = sorted[i];
-    const unsigned key = sortedKey[i];
-    const int cx = (int)(key & ((1u << P.sg_bx) - 1u)), cy = (int)(key >> P.sg_bx);
     // cells reached by the density radius (>= 1 cell each way; more only if the grid was capped)
     const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, P.sg_ny);
-    (void)cx; (void)cy;
     int cnt = 0;
     for (int r = cy0; r <= cy1; r++) {
       int b, e;
-      row_span(sk, rs, r, cx0, cx1, P.sg_bx, b, e);
+      row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
       for (int j = b; j < e; j++) {
         const float4 q = so[j];
         // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
@@ -1472,8 +1498,7 @@ __device__ __forceinline__ bool shape_context_contribution(const float4 o, const
 template <int NT, int CAP, int NB_MIN, bool LAST>
 __global__ void __launch_bounds__(NT) k_desc_hist(
     const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
-    int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted,
-    const unsigned* __restrict__ sortedKey, const int* __restrict__ rowStart,
+    int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted, SurfIndex X,
     const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
     const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
     float* __restrict__ desc, DevCounters* __restrict__ ctr) {
@@ -1524,15 +1549,16 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const float4 o = kpOut[g];
     const long long base = scan_off[s];
     const float4* so = sorted + base;
-    const unsigned* sk = sortedKey + base;
-    const int* rs = rowStart + (long long)s * (P.sg_ny + 1);
+    const unsigned* sk = X.sortedKey + base;
+    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
     const int* rh = rho + base;
     const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
     for (int r0 = cy0; r0 <= cy1; r0 += 32) {  // at most ~12 rows: one pass
       if (w == 0) {
         int b = 0, e = 0;
-        if (r0 + lane <= cy1) row_span(sk, rs, r0 + lane, cx0, cx1, P.sg_bx, b, e);
+        if (r0 + lane <= cy1) row_span(sk, rs, ct, P.sg_nx, r0 + lane, cx0, cx1, P.sg_bx, b, e);
         int inc = e - b;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
