@@ -333,7 +333,7 @@ int ensure_rowstart(fe_ctx* ctx, Slot& s, int nscans) {
   }
   const int64_t ncells = (int64_t)ctx->dp.sg_nx * ctx->dp.sg_ny;
   if (ncells <= SURF_MAX_CELLS) {
-    const int64_t needT = (int64_t)std::max(nscans, s.capScans) * (ncells + 1);
+    const int64_t needT = (int64_t)std::max(nscans, s.capScans) * ((ncells + 2) & ~1LL);
     if (needT > s.capCellTab) {
       if (s.d_cellTab) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.d_cellTab)); s.d_cellTab = nullptr; }
       CK(dalloc(&s.d_cellTab, (size_t)needT));
@@ -350,7 +350,7 @@ SurfIndex surf_index(const fe_ctx* ctx, const Slot& s) {
   X.rowStart = s.d_rowStart;
   X.cellTab = (ncells <= SURF_MAX_CELLS) ? s.d_cellTab : nullptr;
   X.tabOk = s.d_tabOk;
-  X.ncells1 = (int)(ncells + 1);
+  X.ncells1 = (int)((ncells + 2) & ~1LL);
   return X;
 }
 

@@ -1237,7 +1237,8 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
     return;
   }
   if (tid == 0) { surfN[s] = n; tabOk[s] = 1; }
-  unsigned short* tab = cellTab + (long long)s * (ncells + 1);
+  const int tabStride = (ncells + 2) & ~1;  // even: every scan's table is 4-byte aligned
+  unsigned short* tab = cellTab + (long long)s * tabStride;
   if (n == 0) {
     for (int r = tid; r <= ny; r += NT2) rs[r] = 0;
     for (int i = tid; i <= ncells; i += NT2) tab[i] = 0;
@@ -1278,13 +1279,13 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
     if (r < ny) { const int cell = r * nx; const unsigned wv = cells[cell >> 1]; v = (cell & 1) ? (int)(wv >> 16) : (int)(wv & 0xFFFFu); }
     rs[r] = v;
   }
-  // the table of cell starts for K4b-d (32-bit stores of two cells; the table is 4-byte aligned per scan
-  // only when ncells+1 is even, so the tail and odd layouts go element-wise)
-  for (int i = tid; i < ncells; i += NT2) {
-    const unsigned wv = cells[i >> 1];
-    tab[i] = (unsigned short)((i & 1) ? (wv >> 16) : (wv & 0xFFFFu));
+  // the table of cell starts for K4b-d: exactly the packed words (low half = even cell).  With an odd
+  // cell count the spare high half already holds n (the start of the cell after the last one).
+  {
+    unsigned* tabw = (unsigned*)tab;
+    for (int i = tid; i < nwords; i += NT2) tabw[i] = cells[i];
+    if (tid == 0 && (ncells & 1) == 0) tabw[nwords] = (unsigned)n;
   }
-  if (tid == 0) tab[ncells] = (unsigned short)n;
   __syncthreads();
   // (3) scatter: the start of a cell doubles as its cursor (it ends at the cell's end <= n <= 65535,
   //     so a 16-bit half never carries into its neighbour)
@@ -1313,9 +1314,9 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
 struct SurfIndex {
   const unsigned* sortedKey;      // keys of the sorted points (CSR by scan)
   const int* rowStart;            // [scan][ny+1]
-  const unsigned short* cellTab;  // [scan][ncells+1] first slot of every cell (last = n), may be null
+  const unsigned short* cellTab;  // [scan][stride >= ncells+1, even] first slot of every cell (then n), may be null
   const int* tabOk;               // [scan] 1: the scan has a cell table
-  int ncells1;                    // ncells + 1
+  int ncells1;                    // the per-scan stride of cellTab in entries
 };
 
 // span of sorted positions of row r whose cell x is in [cx0, cx1]
