@@ -199,3 +199,40 @@ def test_oversized_rings_take_the_global_memory_path(ob, node):
     co = ob.extract_clusters(pts, 0.65, 5, 50, mode=1)
     cg = node.extractClusters(pts, 0.65, 5, 50)
     assert len(co) == len(cg) and all(np.array_equal(a, b) for a, b in zip(co, cg))
+
+
+def test_descriptors_off_and_parameter_changes_on_a_live_context(ob, synth):
+    """estimate_descriptors=false (src:112) skips the 3DSC stage; fe_set_params re-derives thresholds,
+    grids and tables on an existing context (the reference reads its members on every callback)."""
+    from feature_extraction_b200 import FeatureExtractionNode
+    pts, offs, rp = synth.generate(2, 6, scan_index_base=40)
+    P = ob.node_default()
+    nd = FeatureExtractionNode(to_fe_params(P), max_points=1 << 20, max_scans=16, max_keypoints=4096)
+    ko1, kp1, d1 = nd.processBatch(pts, offs, rp)
+    P.estimate_descriptors = 0
+    nd.set_params(to_fe_params(P))
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    assert d is None and np.array_equal(ko, ko1) and bits_equal(kp, kp1)
+    # launch preset on the same context, then back: results follow the parameters both times
+    L = ob.launch_playback()
+    nd.set_params(to_fe_params(L))
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    ko_o, kp_o, d_o, m = ob.process_batch(L, pts, offs, rp, mode=1, n_threads=4, want_margin=True)
+    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o) and check_descriptors(d, d_o, m)[2] == 0
+    P.estimate_descriptors = 1
+    P.descriptor_radius = 1.5
+    nd.set_params(to_fe_params(P))
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    ko_o, kp_o, d_o, m = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=4, want_margin=True)
+    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o) and check_descriptors(d, d_o, m)[2] == 0
+    nd.close()
+
+
+def test_non_finite_imu_state_yields_no_keypoints(ob, synth, node):
+    """roll/pitch are uninitialised in the reference until the first IMU message: a NaN
+    rotation makes every point non-finite, which the crop drops — empty result, no error."""
+    pts, offs, rp = synth.generate(2, 2, scan_index_base=77)
+    bad = np.array([[np.nan, 0.0], [0.0, np.inf]])
+    ko, kp, d = node.processBatch(pts, offs, bad)
+    ko_o, kp_o, d_o, _ = ob.process_batch(ob.node_default(), pts, offs, bad, mode=1)
+    assert ko[-1] == 0 and ko_o[-1] == 0
