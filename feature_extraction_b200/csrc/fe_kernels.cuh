@@ -152,7 +152,7 @@ struct RawLayout {  // records of fe_point_layout_t; raw == nullptr: the input i
 // per-scan consumers concatenate pieces in order and no global prefix sum is needed.
 // ============================================================================================
 template <bool RAW, bool FUSED>
-__global__ void __launch_bounds__(256, 4) k_level_crop_ring(
+__global__ void __launch_bounds__(256, 6) k_level_crop_ring(
     const float4* __restrict__ pts, const long long* __restrict__ scan_off,
     const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
     int flags_rt, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
 #pragma unroll
   for (int i = 0; i < 9; i++) m[i] = (flags & F_ROT) ? rot[s * 9 + i] : 0.0f;
 
-  float4 o[8];
+  // the 8 transformed points of a thread wait in shared memory (read back by the same thread only):
+  // 32 registers less per thread -> 6 blocks per SM instead of 4
+  __shared__ float4 s_o[8 * 256];
   unsigned code = 0;             // 8 x 4 bits: ring id of round r (first ring containing el)
   unsigned fl = 0;               // bit r: surf, bit 8+r: crop, bit 16+r: dual ring, bit 24+r: no ring
   unsigned ms[8], mc[8];
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
       if (flags & F_SURF)
         fs = fin && q.x >= P.sx0 && q.x <= P.sx1 && q.y >= P.sy0 && q.y <= P.sy1 && q.z >= P.sz0 && q.z <= P.sz1;
     }
-    o[r] = q;
+    s_o[r * 256 + tid] = q;
     if (fs) fl |= 1u << r;
     if (fc) fl |= 1u << (8 + r);
     ms[r] = __ballot_sync(FE_FULL, fs);
@@ -266,14 +268,15 @@ __global__ void __launch_bounds__(256, 4) k_level_crop_ring(
   const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int r = 0; r < 8; r++) {
+    const float4 orr = s_o[r * 256 + tid];
     if (fl & (1u << r)) {
-      float4 sq = o[r];  // 3DSC reads only x,y,z of the surface: .w carries the point's index in the scan
+      float4 sq = orr;  // 3DSC reads only x,y,z of the surface: .w carries the point's index in the scan
       sq.w = __int_as_float(c * CH + w * 256 + r * 32 + lane);
       surf[base + os + __popc(ms[r] & lt)] = sq;
     }
     if (fl & (1u << (8 + r))) {
       const long long d = base + oc + __popc(mc[r] & lt);
-      crop[d] = o[r];
+      crop[d] = orr;
       unsigned cd = (code >> (4 * r)) & 15u;
       if (fl & (1u << (16 + r))) cd |= 16u;
       if (fl & (1u << (24 + r))) cd = 32u;
