@@ -379,7 +379,7 @@ int set_kernel_attrs(fe_ctx* ctx) {
                           (int)desc_smem_bytes(DCAP_M, 512)));
   CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_L, DCAP_M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)desc_smem_bytes(DCAP_L, 512)));
-  CK(cudaFuncSetAttribute(k_surface_grid_cells, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CK(cudaFuncSetAttribute(k_surface_grid_cells<NT_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)surf_cells_smem_bytes(SURF_MAX_CELLS)));
   return FE_OK;
 }
@@ -400,7 +400,7 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
 void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
   const int ncells = P.sg_nx * P.sg_ny;
   if (ncells <= SURF_MAX_CELLS) {
-    k_surface_grid_cells<<<nscans, NT2, surf_cells_smem_bytes(ncells), s.stream>>>(
+    k_surface_grid_cells<NT_SURF><<<nscans, NT_SURF, surf_cells_smem_bytes(ncells), s.stream>>>(
         s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf,
         s.d_cellTab, s.d_tabOk);
     k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,

@@ -1204,10 +1204,12 @@ __global__ void __launch_bounds__(NT2, 2) k_surface_grid(
 // cells (their starts; the row starts fall out of it), then scatter every point to the next free
 // slot of its cell.  Two coalesced sweeps over the scan's surface pieces, no key/value ping-pong.
 // Scans with more than 65,535 surface points (16-bit counters) are deferred to the radix kernel.
+constexpr int NT_SURF = 512;           // threads of the counting-sort K4a (384 was measured: slower)
 constexpr int SURF_MAX_CELLS = 57344;  // 112 KB of counters: 2 blocks / SM at the upper end
 constexpr size_t surf_cells_smem_bytes(int ncells) { return (size_t)((ncells + 1) / 2) * 4 + 64; }
 
-__global__ void __launch_bounds__(NT2) k_surface_grid_cells(
+template <int NTS>
+__global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     const float4* __restrict__ surf, const int* __restrict__ surfCnt,
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
     float4* __restrict__ sorted, unsigned* __restrict__ sortedKey, int* __restrict__ rowStart,
@@ -1218,7 +1220,7 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   __shared__ int sc[40];
   __shared__ int s_n;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  constexpr int NW = NT2 / 32;
+  constexpr int NW = NTS / 32;
   const long long base = scan_off[s];
   const int c0 = chunk_off[s];
   const int nch = chunk_off[s + 1] - c0;
@@ -1227,12 +1229,12 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   // total surface points of the scan
   {
     int v = 0;
-    for (int c = tid; c < nch; c += NT2) v += surfCnt[c0 + c];
+    for (int c = tid; c < nch; c += NTS) v += surfCnt[c0 + c];
     int tot;
-    block_excl_scan<NT2>(v, &tot, sc);
+    block_excl_scan<NTS>(v, &tot, sc);
     if (tid == 0) s_n = tot;
   }
-  for (int i = tid; i < nwords; i += NT2) cells[i] = 0u;
+  for (int i = tid; i < nwords; i += NTS) cells[i] = 0u;
   __syncthreads();
   const int n = s_n;
   if (n > 65535) {
@@ -1243,8 +1245,8 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   const int tabStride = (ncells + 2) & ~1;  // even: every scan's table is 4-byte aligned
   unsigned short* tab = cellTab + (long long)s * tabStride;
   if (n == 0) {
-    for (int r = tid; r <= ny; r += NT2) rs[r] = 0;
-    for (int i = tid; i <= ncells; i += NT2) tab[i] = 0;
+    for (int r = tid; r <= ny; r += NTS) rs[r] = 0;
+    for (int i = tid; i <= ncells; i += NTS) tab[i] = 0;
     return;
   }
   // (1) count: the survivors of a chunk are contiguous; every chunk is cut into 8 slices and the
@@ -1263,12 +1265,12 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   __syncthreads();
   // (2) exclusive scan over the cells in key order; every thread owns a run of whole words
   {
-    const int per = (nwords + NT2 - 1) / NT2;
+    const int per = (nwords + NTS - 1) / NTS;
     const int wb = min(tid * per, nwords), we = min(wb + per, nwords);
     int sum = 0;
     for (int i = wb; i < we; i++) { const unsigned v = cells[i]; sum += (int)(v & 0xFFFFu) + (int)(v >> 16); }
     int tot;
-    int run = block_excl_scan<NT2>(sum, &tot, sc);
+    int run = block_excl_scan<NTS>(sum, &tot, sc);
     for (int i = wb; i < we; i++) {
       const unsigned v = cells[i];
       const int lo = (int)(v & 0xFFFFu), hi = (int)(v >> 16);
@@ -1277,7 +1279,7 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
     }
   }
   __syncthreads();
-  for (int r = tid; r <= ny; r += NT2) {
+  for (int r = tid; r <= ny; r += NTS) {
     int v = n;
     if (r < ny) { const int cell = r * nx; const unsigned wv = cells[cell >> 1]; v = (cell & 1) ? (int)(wv >> 16) : (int)(wv & 0xFFFFu); }
     rs[r] = v;
@@ -1286,7 +1288,7 @@ __global__ void __launch_bounds__(NT2) k_surface_grid_cells(
   // cell count the spare high half already holds n (the start of the cell after the last one).
   {
     unsigned* tabw = (unsigned*)tab;
-    for (int i = tid; i < nwords; i += NT2) tabw[i] = cells[i];
+    for (int i = tid; i < nwords; i += NTS) tabw[i] = cells[i];
     if (tid == 0 && (ncells & 1) == 0) tabw[nwords] = (unsigned)n;
   }
   __syncthreads();
