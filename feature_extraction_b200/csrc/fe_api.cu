@@ -4,9 +4,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fe_kernels.cuh"
@@ -1181,6 +1183,106 @@ int fe_pack_point_descriptors(const fe_point_t* keypoints, const float* descript
     memcpy(r + 5, descriptors + i * FE_DESC_LEN, FE_DESC_LEN * sizeof(float));
     // rf[9] at r + 5 + 1980 stays zero (3dsc.hpp zeroes it); 2 floats of tail padding (EIGEN_ALIGN16)
   }
+  return FE_OK;
+}
+
+// ---- scan-parallel sharding over several GPUs in one process -----------------------------------------
+struct fe_multi {
+  std::vector<fe_ctx_t*> ctx;
+  std::vector<int64_t> kpOffsets;
+  fe_point_t* kp = nullptr;   // gathered results: plain malloc'd buffers grown on demand (no zero fill)
+  float* desc = nullptr;
+  int64_t capKp = 0, capDesc = 0;
+  std::string err;
+};
+
+int fe_multi_create(const int32_t* devices, int32_t n_devices, const fe_params_t* params,
+                    const fe_limits_t* limits, fe_multi_t** out) {
+  if (!out || !devices || n_devices < 1 || !params) return FE_ERR_INVALID;
+  *out = nullptr;
+  fe_multi* m = new fe_multi();
+  for (int g = 0; g < n_devices; g++) {
+    fe_ctx_t* c = nullptr;
+    const int st = fe_create(devices[g], params, limits, &c);
+    if (st != FE_OK) { fe_multi_destroy(m); return st; }
+    m->ctx.push_back(c);
+  }
+  *out = m;
+  return FE_OK;
+}
+
+void fe_multi_destroy(fe_multi_t* m) {
+  if (!m) return;
+  for (fe_ctx_t* c : m->ctx) fe_destroy(c);
+  free(m->kp);
+  free(m->desc);
+  delete m;
+}
+
+const char* fe_multi_last_error(const fe_multi_t* m) { return m ? m->err.c_str() : "null context"; }
+
+int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_t* scan_offsets,
+                           const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out) {
+  if (!m || !out || n_scans < 0 || (n_scans > 0 && (!scan_offsets || !roll_pitch))) return FE_ERR_INVALID;
+  const int G = (int)m->ctx.size();
+  m->err.clear();
+  std::vector<fe_batch_result_t> res(G);
+  std::vector<int> status(G, FE_OK);
+  std::vector<int> lo(G + 1);
+  for (int g = 0; g <= G; g++) lo[g] = (int)(((int64_t)n_scans * g) / G);
+  {  // one host thread per GPU: its shard through fe_process_batch (absolute offsets into `points`)
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+      th.emplace_back([&, g]() {
+        status[g] = fe_process_batch(m->ctx[g], points, scan_offsets + lo[g], roll_pitch ? roll_pitch + 2 * (int64_t)lo[g] : nullptr,
+                                     lo[g + 1] - lo[g], &res[g]);
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int g = 0; g < G; g++)
+    if (status[g] != FE_OK) {
+      m->err = std::string("device shard ") + std::to_string(g) + ": " + fe_last_error(m->ctx[g]);
+      return status[g];
+    }
+  // host-side gather in scan order
+  std::vector<int64_t> kbase(G + 1, 0);
+  for (int g = 0; g < G; g++) kbase[g + 1] = kbase[g] + res[g].n_keypoints;
+  const int64_t K = kbase[G];
+  const bool desc = m->ctx[0]->params.estimate_descriptors != 0;
+  m->kpOffsets.assign((size_t)n_scans + 1, 0);
+  if (K > m->capKp) {
+    free(m->kp);
+    m->capKp = K + K / 2 + 1024;
+    m->kp = (fe_point_t*)malloc((size_t)m->capKp * sizeof(fe_point_t));
+    if (!m->kp) { m->capKp = 0; m->err = "out of host memory"; return FE_ERR_CAPACITY; }
+  }
+  if (desc && K > m->capDesc) {
+    free(m->desc);
+    m->capDesc = K + K / 2 + 1024;
+    m->desc = (float*)malloc((size_t)m->capDesc * FE_DESC_LEN * sizeof(float));
+    if (!m->desc) { m->capDesc = 0; m->err = "out of host memory"; return FE_ERR_CAPACITY; }
+  }
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+      th.emplace_back([&, g]() {
+        const int ns = lo[g + 1] - lo[g];
+        for (int i = 0; i <= ns; i++) m->kpOffsets[lo[g] + i] = kbase[g] + res[g].keypoint_offsets[i];
+        if (res[g].n_keypoints > 0) {
+          memcpy(m->kp + kbase[g], res[g].keypoints, (size_t)res[g].n_keypoints * sizeof(fe_point_t));
+          if (desc) memcpy(m->desc + kbase[g] * FE_DESC_LEN, res[g].descriptors, (size_t)res[g].n_keypoints * FE_DESC_LEN * sizeof(float));
+        }
+      });
+    for (auto& t : th) t.join();
+  }
+  out->n_scans = n_scans;
+  out->n_keypoints = K;
+  out->keypoint_offsets = m->kpOffsets.data();
+  out->keypoints = m->kp;
+  out->descriptors = desc ? m->desc : nullptr;
+  out->on_device = 0;
+  out->gpu_launches = 0;
+  for (int g = 0; g < G; g++) out->gpu_launches += res[g].gpu_launches;
   return FE_OK;
 }
 

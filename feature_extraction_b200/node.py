@@ -296,6 +296,51 @@ class FeatureExtractionNode:
         return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
 
 
+class MultiGpuExtractor:
+    """fe_multi_*: scans sharded over several GPUs of one box in ONE process (a host thread and a
+    context per GPU, contiguous scan ranges, host-side CSR gather; no collective)."""
+
+    def __init__(self, devices, params=None, max_points=0, max_scans=0, max_keypoints=0, max_ring_clusters=0):
+        self._m = C.c_void_p()
+        self.params = (params or node_default()).copy()
+        dev = np.ascontiguousarray(devices, np.int32)
+        lim = N.Limits(max_points, max_scans, max_keypoints, max_ring_clusters)
+        st = N.lib().fe_multi_create(_ptr(dev), len(dev), C.byref(self.params), C.byref(lim), C.byref(self._m))
+        if st != N.FE_OK:
+            self._m = C.c_void_p()
+            raise FeatureExtractionError(st, "fe_multi_create failed")
+
+    def close(self):
+        if self._m:
+            N.lib().fe_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def processBatch(self, points, scan_offsets, roll_pitch):
+        c = _cloud(points)
+        offs = np.ascontiguousarray(scan_offsets, np.int64)
+        rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
+        B = len(offs) - 1
+        res = N.BatchResult()
+        st = N.lib().fe_multi_process_batch(self._m, _ptr(c), _ptr(offs), _ptr(rp), B, C.byref(res))
+        if st != N.FE_OK:
+            raise FeatureExtractionError(st, (N.lib().fe_multi_last_error(self._m) or b"").decode())
+        K = int(res.n_keypoints)
+        ko = np.ctypeslib.as_array(res.keypoint_offsets, shape=(B + 1,)).copy()
+        kp = np.zeros((0, 4), np.float32)
+        d = np.zeros((0, DESC_LEN), np.float32) if self.params.estimate_descriptors else None
+        if K > 0:
+            kp = np.ctypeslib.as_array(C.cast(res.keypoints, C.POINTER(C.c_float)), shape=(K, 4)).copy()
+            if res.descriptors:
+                d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, DESC_LEN)).copy()
+        return ko, kp, d
+
+
 def imu_to_roll_pitch(quat_xyzw, cloud_leveling=True):
     """imuCallback (src:57-70): quaternion {x,y,z,w} -> (roll, pitch) as the node stores them."""
     q = np.ascontiguousarray(quat_xyzw, np.float64)

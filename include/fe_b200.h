@@ -133,6 +133,18 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points,
                             const int64_t* scan_offsets, const double* roll_pitch,
                             int32_t n_scans, fe_batch_result_t* out);
 
+/* ---- scan-parallel sharding over several GPUs of one box, in one process -------- */
+/* Scans are independent (src:72-145 reads no cross-scan state): GPU g of G takes the contiguous scan
+ * range [g*B/G, (g+1)*B/G), one host thread and one context per GPU, and the per-GPU results are
+ * concatenated on the host in scan order.  No collective is involved. */
+typedef struct fe_multi fe_multi_t;
+int fe_multi_create(const int32_t* devices, int32_t n_devices, const fe_params_t* params,
+                    const fe_limits_t* limits, fe_multi_t** out);
+int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_t* scan_offsets,
+                           const double* roll_pitch, int32_t n_scans, fe_batch_result_t* out);
+void fe_multi_destroy(fe_multi_t* m);
+const char* fe_multi_last_error(const fe_multi_t* m);
+
 /* Copy `bytes` of a device-resident result (fe_process_batch_device) to host memory. */
 int fe_download(fe_ctx_t* ctx, void* host_dst, const void* device_src, int64_t bytes);
 

@@ -181,3 +181,18 @@ def test_descriptors_are_bit_identical_when_summed_in_pcl_order(ob, synth, nodes
                 total += 1
                 exact += int(bits_equal(dg[i], r["descriptors"][i]))
     assert total > 0 and exact == total, (exact, total)
+
+
+def test_in_process_multi_gpu_sharding_equals_single_context(ob, synth, nodes):
+    """fe_multi_*: every visible GPU (at least one) gets a contiguous scan range; the gathered CSR result
+    equals the single-context result."""
+    import torch
+    from feature_extraction_b200 import MultiGpuExtractor
+    nd = nodes(2)
+    pts, offs, rp = synth.generate(2, 23, scan_index_base=1200)
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    for devs in ([0], list(range(torch.cuda.device_count())), [0, 0, 0]):
+        m = MultiGpuExtractor(devs, to_fe_params(_params(ob, 2)), max_points=4 << 20, max_scans=64, max_keypoints=4096)
+        ko2, kp2, d2 = m.processBatch(pts, offs, rp)
+        m.close()
+        assert np.array_equal(ko, ko2) and bits_equal(kp, kp2) and bits_equal(d, d2)

@@ -155,3 +155,15 @@ def test_null_and_invalid_arguments_are_status_codes_not_crashes():
     assert L.fe_last_error(None) == b"null context"
     lay = N.PointLayout(8, 0, 4, 8)
     assert L.fe_process_batch_layout(None, None, C.byref(lay), None, None, 0, C.byref(res)) == N.FE_ERR_INVALID
+
+
+def test_multi_gpu_helper_rejects_bad_arguments():
+    from feature_extraction_b200 import _native as N, node_default
+    L = N.lib()
+    m = C.c_void_p()
+    P = node_default()
+    assert L.fe_multi_create(None, 0, C.byref(P), None, C.byref(m)) == N.FE_ERR_INVALID
+    res = N.BatchResult()
+    assert L.fe_multi_process_batch(None, None, None, None, 0, C.byref(res)) == N.FE_ERR_INVALID
+    L.fe_multi_destroy(None)
+    assert L.fe_multi_last_error(None) == b"null context"
