@@ -321,7 +321,7 @@ class MultiGpuExtractor:
         except Exception:
             pass
 
-    def processBatch(self, points, scan_offsets, roll_pitch):
+    def processBatch(self, points, scan_offsets, roll_pitch, copy=True):
         c = _cloud(points)
         offs = np.ascontiguousarray(scan_offsets, np.int64)
         rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
@@ -335,9 +335,12 @@ class MultiGpuExtractor:
         kp = np.zeros((0, 4), np.float32)
         d = np.zeros((0, DESC_LEN), np.float32) if self.params.estimate_descriptors else None
         if K > 0:
-            kp = np.ctypeslib.as_array(C.cast(res.keypoints, C.POINTER(C.c_float)), shape=(K, 4)).copy()
+            kp = np.ctypeslib.as_array(C.cast(res.keypoints, C.POINTER(C.c_float)), shape=(K, 4))
             if res.descriptors:
-                d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, DESC_LEN)).copy()
+                d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, DESC_LEN))
+            if copy:
+                kp = kp.copy()
+                d = d.copy() if d is not None else None
         return ko, kp, d
 
 
