@@ -236,3 +236,35 @@ def test_non_finite_imu_state_yields_no_keypoints(ob, synth, node):
     ko, kp, d = node.processBatch(pts, offs, bad)
     ko_o, kp_o, d_o, _ = ob.process_batch(ob.node_default(), pts, offs, bad, mode=1)
     assert ko[-1] == 0 and ko_o[-1] == 0
+
+
+def test_random_parameter_sets_match_the_oracle(ob, synth):
+    """Derived constants (grid sizes and caps, key widths, trusted-cell flag, surface box, shape-context
+    tables) must hold for arbitrary ROS parameter values, not just the two presets."""
+    from feature_extraction_b200 import FeatureExtractionNode
+    rng = np.random.default_rng(2024)
+    scans = {2: synth.generate(2, 2, scan_index_base=600), 3: synth.generate(3, 1, scan_index_base=601)}
+    nd = None
+    for trial in range(14):
+        P = ob.node_default()
+        P.x_min = float(rng.uniform(-60, 5)); P.x_max = float(P.x_min + rng.uniform(8, 120))
+        P.y_min = float(rng.uniform(-60, -2)); P.y_max = float(rng.uniform(2, 60))
+        P.z_min = float(rng.uniform(-2.2, -0.5)); P.z_max = float(rng.uniform(0.5, 8))
+        P.cluster_tolerance = float(rng.choice([0.05, 0.2, 0.65, 1.0, 2.0]))
+        P.cluster_min_count = int(rng.integers(1, 8)); P.cluster_max_count = int(rng.choice([10, 50, 400, 2000]))
+        P.cluster_radius_threshold = float(rng.uniform(0.05, 0.6))
+        P.number_detection_channels = int(rng.integers(1, 5))
+        P.descriptor_radius = float(rng.choice([0.3, 1.0, 2.5, 4.0, 6.0]))
+        cfg = 3 if trial % 4 == 3 else 2
+        pts, offs, rp = scans[cfg]
+        if nd is None:
+            nd = FeatureExtractionNode(to_fe_params(P), max_points=1 << 21, max_scans=8, max_keypoints=1 << 14)
+        else:
+            nd.set_params(to_fe_params(P))
+        ko, kp, d = nd.processBatch(pts, offs, rp)
+        ko_o, kp_o, d_o, m = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=8, want_margin=True)
+        tag = (trial, P.cluster_tolerance, P.cluster_radius_threshold, P.descriptor_radius, int(ko_o[-1]))
+        assert np.array_equal(ko, ko_o), tag
+        assert bits_equal(kp, kp_o), tag
+        assert check_descriptors(d, d_o, m)[2] == 0, tag
+    nd.close()
