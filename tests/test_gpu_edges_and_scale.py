@@ -268,3 +268,21 @@ def test_random_parameter_sets_match_the_oracle(ob, synth):
         assert bits_equal(kp, kp_o), tag
         assert check_descriptors(d, d_o, m)[2] == 0, tag
     nd.close()
+
+
+def test_very_large_scan_takes_the_deferred_paths(ob, synth):
+    """One scan with > 65,535 surface points (beyond the 16-bit cell counters of the counting-sort K4a)
+    and a symmetric crop: the deferred instantiations (radix K4a, large K2) must give the same result."""
+    from feature_extraction_b200 import FeatureExtractionNode
+    pts, offs, rp = synth.generate(3, 1, scan_index_base=77, azimuth_steps=14400)
+    assert len(pts) > 100000
+    P = ob.node_default()
+    P.x_min = -75.0
+    nd = FeatureExtractionNode(to_fe_params(P), max_points=1 << 20, max_scans=4, max_keypoints=1 << 14)
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    # device-side counters of this call come from the host path's slot 0
+    r = ob.process_scan(P, pts, rp[0, 0], rp[0, 1], mode=1)
+    assert len(r["cloud_full"]) == len(pts)
+    assert bits_equal(kp, r["keypoints"])
+    assert check_descriptors(d, r["descriptors"], r["edge_margin"])[2] == 0
+    nd.close()
