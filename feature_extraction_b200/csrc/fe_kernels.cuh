@@ -162,6 +162,11 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
   const int flags = FUSED ? (F_ELEV | F_ROT | F_CROP | F_RING | (flags_rt & F_SURF)) : flags_rt;
   __shared__ int s_scan;
   __shared__ int s_ws[8], s_wc[8];
+  // One tile of shared memory holds the chunk twice over: first its input points, brought in by a single
+  // TMA bulk copy (float4 input), then — slot by slot, each written by the thread that read it — the
+  // transformed points waiting for their output offsets.
+  __shared__ __align__(128) float4 s_o[CH];
+  __shared__ __align__(8) unsigned long long s_bar;
   const int chunk = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) {
@@ -171,19 +176,24 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
       if (chunk_off[mid] <= chunk) lo = mid; else hi = mid - 1;
     }
     s_scan = lo;
+    if (!RAW) {
+      const long long b0 = scan_off[lo] + (long long)(chunk - chunk_off[lo]) * CH;
+      const int n0 = (int)min((long long)CH, scan_off[lo + 1] - b0);
+      mbar_init(&s_bar, 1);
+      mbar_expect_tx(&s_bar, (unsigned)n0 * 16u);
+      tma_load_1d(s_o, pts + b0, (unsigned)n0 * 16u, &s_bar);
+    }
   }
   __syncthreads();
   const int s = s_scan;
   const int c = chunk - chunk_off[s];
   const long long base = scan_off[s] + (long long)c * CH;
   const int nIn = (int)min((long long)CH, scan_off[s + 1] - base);
+  if (!RAW) mbar_wait(&s_bar, 0);
   float m[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) m[i] = (flags & F_ROT) ? rot[s * 9 + i] : 0.0f;
 
-  // the 8 transformed points of a thread wait in shared memory (read back by the same thread only):
-  // 32 registers less per thread -> 6 blocks per SM instead of 4
-  __shared__ float4 s_o[8 * 256];
   unsigned code = 0;             // 8 x 4 bits: ring id of round r (first ring containing el)
   unsigned fl = 0;               // bit r: surf, bit 8+r: crop, bit 16+r: dual ring, bit 24+r: no ring
   unsigned ms[8], mc[8];
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
         const unsigned char* rec = L.raw + (base + j) * (long long)L.stride;
         p = make_float4(load_f32_any(rec + L.xo), load_f32_any(rec + L.yo), load_f32_any(rec + L.zo), 0.0f);
       } else {
-        p = __ldg(pts + base + j);
+        p = s_o[j];
       }
       float el = p.w;
       if (flags & F_ROT) {
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
       if (flags & F_SURF)
         fs = fin && q.x >= P.sx0 && q.x <= P.sx1 && q.y >= P.sy0 && q.y <= P.sy1 && q.z >= P.sz0 && q.z <= P.sz1;
     }
-    s_o[r * 256 + tid] = q;
+    s_o[j] = q;
     if (fs) fl |= 1u << r;
     if (fc) fl |= 1u << (8 + r);
     ms[r] = __ballot_sync(FE_FULL, fs);
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
   const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    const float4 orr = s_o[r * 256 + tid];
+    const float4 orr = s_o[w * 256 + r * 32 + lane];
     if (fl & (1u << r)) {
       float4 sq = orr;  // 3DSC reads only x,y,z of the surface: .w carries the point's index in the scan
       sq.w = __int_as_float(c * CH + w * 256 + r * 32 + lane);
