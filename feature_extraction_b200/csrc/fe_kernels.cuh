@@ -1266,10 +1266,18 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     const int cnt = surfCnt[c0 + c];
     const int j1 = (cnt * (sl + 1)) >> 3;
     const float4* src = surf + base + (long long)c * CH;
-    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 32) {
-      const float4 q = src[j];
-      const int cell = surf_cell(q.y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q.x, P.sx0, P.sg_inv, nx);
-      atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
+    // four loads in flight per lane: the sweep is latency-bound, not bandwidth-bound
+    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 128) {
+      float4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (j + 32 * k < j1) {
+          const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
+          atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
+        }
+      }
     }
   }
   __syncthreads();
@@ -1311,14 +1319,21 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     const int cnt = surfCnt[c0 + c];
     const int j1 = (cnt * (sl + 1)) >> 3;
     const float4* src = surf + base + (long long)c * CH;
-    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 32) {
-      const float4 q = src[j];
-      const int cx = surf_cell(q.x, P.sx0, P.sg_inv, nx), cy = surf_cell(q.y, P.sy0, P.sg_inv, ny);
-      const int cell = cy * nx + cx;
-      const unsigned old = atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
-      const int pos = (cell & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu);
-      so[pos] = q;
-      sk[pos] = ((unsigned)cy << P.sg_bx) | (unsigned)cx;
+    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 128) {
+      float4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (j + 32 * k < j1) {
+          const int cx = surf_cell(q[k].x, P.sx0, P.sg_inv, nx), cy = surf_cell(q[k].y, P.sy0, P.sg_inv, ny);
+          const int cell = cy * nx + cx;
+          const unsigned old = atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
+          const int pos = (cell & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu);
+          so[pos] = q[k];
+          sk[pos] = ((unsigned)cy << P.sg_bx) | (unsigned)cx;
+        }
+      }
     }
   }
 }
