@@ -441,6 +441,10 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
     kS = ko; kT = ki; vS = vo; vT = vi;
   }
   __syncthreads();
+  // The last pass leaves in S.base[d] the end offset of top digit d: a 256-bucket index into the
+  // sorted keys that shortens every lower_bound below (keybits == 0: one bucket, no pass ran).
+  const int topShift = (keybits > 0) ? 8 * ((keybits - 1) >> 3) : 32;
+  const unsigned* bucketEnd = S.base;
   // ---- units: the runs of equal key (cells); every entry on its own when cells are not trusted ----
   unsigned short* unitStart = S.lst;
   int nU = 0;
@@ -452,6 +456,7 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
       int tot;
       const int pos = block_excl_scan<NT>(head, &tot, sc);
       if (head) unitStart[run + pos] = (unsigned short)p;
+      if (p < E) S.aux[p] = (unsigned short)(run + pos + head - 1);  // unit index of every sorted position
       run += tot;
     }
     nU = run;
@@ -462,12 +467,8 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
   constexpr int G = 8;
   const int gl = lane & (G - 1);
   const unsigned gmask = 0xFFu << (lane & 24);
-  unsigned short* unitOf = S.aux;  // unit index of every sorted position
-  for (int u = tid / G; u < nU; u += NT / G) {
-    const int a0 = unitStart[u];
-    const int a1 = (u + 1 < nU) ? (int)unitStart[u + 1] : E;
-    for (int p = a0 + gl; p < a1; p += G) { parentS[p] = (unsigned)a0; unitOf[p] = (unsigned short)u; }
-  }
+  unsigned short* unitOf = S.aux;
+  for (int p = tid; p < E; p += NT) parentS[p] = (unsigned)unitStart[unitOf[p]];
   __syncthreads();
   // One 8-lane group per unit.  The 13 rows (dz,dy) that precede the unit's own cell in key order
   // and can hold linked points are located by 13 binary searches spread over the lanes; the
@@ -505,7 +506,12 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
           const unsigned klo = rowk + (unsigned)max(cx - 2, 0);
           khi[rnd] = rowk + (unsigned)min(cx + 2, nx - 1);
           end[rnd] = (r == 12) ? a0 : E;
-          int l = 0, h = end[rnd];  // lower_bound(klo) in kS[0, end)
+          int l = 0, h = end[rnd];  // lower_bound(klo) in kS[0, end), inside klo's top-digit bucket
+          if (topShift < 32) {
+            const unsigned d = klo >> topShift;
+            l = min(d ? (int)bucketEnd[d - 1] : 0, h);
+            h = min((int)bucketEnd[d], h);
+          }
           while (l < h) {
             const int mid = (l + h) >> 1;
             if (kS[mid] < klo) l = mid + 1; else h = mid;
@@ -799,49 +805,54 @@ __device__ void cluster_rings_scan(
       // ---- getCylinderSegments gate + centroid per cluster (src:282-325), one thread each ----
       int* sh = sc + 100;  // [0] = pool base, [1] = kc base
       int runG = 0, runM = 0;
-      // pass 1 counts, pass 2 writes; the per-cluster result is cached in registers per tile
+      // pass 0 counts, pass 1 writes; with a single tile of clusters (the usual case) pass 1 reuses
+      // the registers of pass 0 instead of walking the member lists again
+      const bool oneTile = (C.nC <= NT);
+      int ok = 0, size = 0, pg = 0, pm = 0;
+      float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int pass = 0; pass < 2; pass++) {
         int accG = 0, accM = 0;
         for (int i0 = 0; i0 < C.nC; i0 += NT) {
           const int i = i0 + tid;
-          int ok = 0, size = 0;
-          float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < C.nC) {
-            const unsigned root = C.slotRoot[i];
-            size = (int)C.cnt[root];
-            const int st = C.slotStart[i];
-            double sumx = 0.0, sumy = 0.0, sumz = 0.0;
-            double minx = 1000.0, maxx = -1000.0, miny = 1000.0, maxy = -1000.0;
-            for (int j = 0; j < size; j++) {
-              const int e = C.mem[st + j];
-              const double x = S.x[e], y = S.y[e], z = S.z[e];
-              sumx += x; sumy += y; sumz += z;
-              if (x < minx) minx = x;
-              if (y < miny) miny = y;
-              if (x > maxx) maxx = x;
-              if (y > maxy) maxy = y;
+          int tg = 0, tm = 0;
+          if (pass == 0 || !oneTile) {
+            ok = 0; size = 0;
+            cen = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < C.nC) {
+              const unsigned root = C.slotRoot[i];
+              size = (int)C.cnt[root];
+              const int st = C.slotStart[i];
+              double sumx = 0.0, sumy = 0.0, sumz = 0.0;
+              double minx = 1000.0, maxx = -1000.0, miny = 1000.0, maxy = -1000.0;
+              for (int j = 0; j < size; j++) {
+                const int e = C.mem[st + j];
+                const double x = S.x[e], y = S.y[e], z = S.z[e];
+                sumx += x; sumy += y; sumz += z;
+                if (x < minx) minx = x;
+                if (y < miny) miny = y;
+                if (x > maxx) maxx = x;
+                if (y > maxy) maxy = y;
+              }
+              const double ddx = maxx - minx, ddy = maxy - miny;
+              const double diameter = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+              if (diameter < P.two_radius_threshold) {
+                ok = 1;
+                cen.x = (float)(sumx / (double)size);
+                cen.y = (float)(sumy / (double)size);
+                cen.z = (float)(sumz / (double)size);
+              }
             }
-            const double ddx = maxx - minx, ddy = maxy - miny;
-            const double diameter = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
-            if (diameter < P.two_radius_threshold) {
-              ok = 1;
-              cen.x = (float)(sumx / (double)size);
-              cen.y = (float)(sumy / (double)size);
-              cen.z = (float)(sumz / (double)size);
-              if (pass == 1) cen.w = crop[S.gref[root]].w;  // intensity of indices[0] (src:320)
-            }
+            pg = block_excl_scan<NT>(ok, &tg, sc);
+            if (kcPool) pm = block_excl_scan<NT>(ok ? size : 0, &tm, sc);
           }
-          int tg, tm;
-          const int pg = block_excl_scan<NT>(ok, &tg, sc);
-          int pm = 0;
-          if (kcPool) pm = block_excl_scan<NT>(ok ? size : 0, &tm, sc); else tm = 0;
           if (pass == 1 && ok) {
             const int b = sh[0];
-            if (b >= 0) kfPool[b + accG + pg] = cen;
+            if (b >= 0) {
+              cen.w = crop[S.gref[C.slotRoot[i]]].w;  // intensity of indices[0] (src:320)
+              kfPool[b + accG + pg] = cen;
+            }
             if (kcPool && sh[1] >= 0) {
-              const unsigned root = C.slotRoot[i];
               const int st = C.slotStart[i];
-              (void)root;
               for (int j = 0; j < size; j++) kcPool[sh[1] + accM + pm + j] = crop[S.gref[C.mem[st + j]]];
             }
           }
