@@ -737,35 +737,43 @@ __device__ void cluster_rings_scan(
   if (nch > MAXCHUNK) { if (tid == 0) atomicOr(&ctr->err, ERR_CHUNKS); return; }
   const int Nc = chunk_prefix<NT>(cropCnt + chunk_off[s], nch, pre, sc);
   if (Nc == 0) return;
-  // entries per ring
-  if (tid < 16) ringCnt[tid] = 0;
-  __syncthreads();
-  for (int i = tid; i < Nc; i += NT) {
-    const unsigned cd = cropMeta[piece_pos(pre, nch, i, base)] & 63u;
-    if (cd & 32u) continue;
-    const int r = single_ring ? 0 : (int)(cd & 15u);
-    atomicAdd(&ringCnt[r], 1);
-    if ((cd & 16u) && !single_ring) atomicAdd(&ringCnt[r + 1], 1);
-  }
-  __syncthreads();
   const int nRingsAll = single_ring ? 1 : 16;
-  {
-    int big = 0;
-    for (int r = 0; r < nRingsAll; r++) big = max(big, ringCnt[r]);
-    if (big > CAP) {  // a single ring is larger than this instantiation's capacity
-      if (tid == 0) {
-        if (ovfList) ovfList[atomicAdd(ovfCount, 1)] = s;  // the next larger instantiation takes it
-        else atomicOr(&ctr->err, ERR_RING_CAP);
-      }
-      return;
-    }
-  }
+  // Entries per ring are only counted when needed: a scan with at most CAP crop survivors is first
+  // gathered whole (all rings, one group); the count and the ring groups are the fallback when the
+  // doubled end-point entries push it over the capacity.
+  bool counted = false, whole = (Nc <= CAP);
   int group = 0;
   int r0 = 0;
   while (r0 < nRingsAll) {
-    // greedy run of consecutive rings that fits the shared-memory capacity
     int r1 = r0, tot = 0;
-    while (r1 < nRingsAll && tot + ringCnt[r1] <= CAP) { tot += ringCnt[r1]; r1++; }
+    if (whole) {
+      r1 = nRingsAll; tot = Nc;
+    } else {
+      if (!counted) {
+        counted = true;
+        if (tid < 16) ringCnt[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < Nc; i += NT) {
+          const unsigned cd = cropMeta[piece_pos(pre, nch, i, base)] & 63u;
+          if (cd & 32u) continue;
+          const int r = single_ring ? 0 : (int)(cd & 15u);
+          atomicAdd(&ringCnt[r], 1);
+          if ((cd & 16u) && !single_ring) atomicAdd(&ringCnt[r + 1], 1);
+        }
+        __syncthreads();
+        int big = 0;
+        for (int r = 0; r < nRingsAll; r++) big = max(big, ringCnt[r]);
+        if (big > CAP) {  // a single ring is larger than this instantiation's capacity
+          if (tid == 0) {
+            if (ovfList) ovfList[atomicAdd(ovfCount, 1)] = s;  // the next larger instantiation takes it
+            else atomicOr(&ctr->err, ERR_RING_CAP);
+          }
+          return;
+        }
+      }
+      // greedy run of consecutive rings that fits the shared-memory capacity
+      while (r1 < nRingsAll && tot + ringCnt[r1] <= CAP) { tot += ringCnt[r1]; r1++; }
+    }
     if (tot > 0) {
       // ---- gather the entries of rings [r0, r1) in original order ----
       int run = 0;
@@ -787,7 +795,7 @@ __device__ void cluster_rings_scan(
         }
         int t2;
         const int pos = block_excl_scan<NT>(take, &t2, sc);
-        if (take) {
+        if (take && run + pos + take <= CAP) {  // the bound only bites on the uncounted attempt
           const float4 q = crop[pp];
           int e = run + pos;
           S.x[e] = q.x; S.y[e] = q.y; S.z[e] = q.z; S.gref[e] = (unsigned)pp; S.ring[e] = (unsigned char)(ra - r0);
@@ -798,6 +806,8 @@ __device__ void cluster_rings_scan(
         }
         run += t2;
       }
+      __syncthreads();
+      if (run > CAP) { whole = false; continue; }  // uncounted attempt did not fit: count, then go ring group by ring group
       __syncthreads();
       const int E = run;
       ClusterOut C;

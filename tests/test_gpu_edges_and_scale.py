@@ -79,6 +79,24 @@ def test_point_on_a_ring_boundary_belongs_to_both_rings(ob, node):
     assert bits_equal(kp_g, kp_o) and bits_equal(kc_g, kc_o)
 
 
+def test_boundary_points_overflow_the_whole_scan_gather_and_fall_back_to_ring_groups(ob, node):
+    # 1200 crop survivors fit the fast ring-clustering capacity (1408 entries), but 720 of them sit on
+    # ring boundaries and count twice: the uncounted whole-scan gather must give way to ring groups
+    rng = np.random.default_rng(5)
+    c = []
+    for k in range(240):
+        cx, cy = rng.uniform(5, 70), rng.uniform(-28, 28)
+        elev = [-14.0, -12.0, -15.0, -10.0, -13.0][k % 5]  # 3 of 5 clusters are on a boundary
+        for j in range(5):
+            c.append((cx + 0.03 * j, cy + rng.uniform(-0.02, 0.02), rng.uniform(-1.0, 2.0) * 0.01, elev))
+    c = np.array(c, np.float32)
+    P = ob.node_default()
+    kp_o, kc_o, kf_o = ob.estimate_keypoints(P, c)
+    kp_g, kc_g = node.estimateKeypoints(c)
+    assert len(kf_o) > 200
+    assert bits_equal(kp_g, kp_o) and bits_equal(kc_g, kc_o)
+
+
 def test_zero_neighbour_keypoint_gives_nan_descriptor(ob, node):
     P = ob.node_default()
     cloud = np.array([[10, 0, 0, 0], [10.2, 0, 0.1, 0], [10.1, 0.3, 0.0, 0]], np.float32)
