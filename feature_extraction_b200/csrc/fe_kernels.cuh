@@ -84,6 +84,7 @@ struct DevCounters {
   int desc_unordered;  // keypoints with more than DCAP_L contributions (summed with atomics, not in PCL's order)
   int ovf_merge2;      // scans deferred from the large K3 to the global-memory instantiation
   int pad[1];
+  unsigned long long nbr_cursor;  // neighbour-list pool (K4b -> K4d)
 };
 
 // getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
@@ -1391,22 +1392,31 @@ __device__ __forceinline__ void row_span(const unsigned* __restrict__ sk, const 
 
 // ============================================================================================
 // K4b — mark the surface points inside the search sphere of any keypoint (3dsc.hpp
-// searchForNeighbors with search_radius_), count each keypoint's neighbours.
+// searchForNeighbors with search_radius_), count each keypoint's neighbours and hand their sorted
+// positions to K4d: the list is collected in shared memory and copied to a slice of `nbrPool`
+// reserved with one atomic (kpNbrOff[g] = first slot, or -1 when a warp found more than
+// MARK_WCAP or the pool is full — K4d then finds the neighbours itself).
 // rho[i] = -(scan+1) marks "density needed".  One block per keypoint, grid-stride.
 // ============================================================================================
+constexpr int MARK_WCAP = 512;            // list entries per warp (16 KB per block: 8 blocks / SM stay resident)
+constexpr int MARK_LCAP = 8 * MARK_WCAP;  // longer lists: K4d's larger instantiations find the neighbours themselves
+
 __global__ void __launch_bounds__(256) k_desc_mark(
     const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
     int n_scans, const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P,
-    int* __restrict__ rho, int* __restrict__ kpNbr) {
-  __shared__ int s_cnt;
+    int* __restrict__ rho, int* __restrict__ kpNbr, unsigned* __restrict__ nbrPool, long long nbrCap,
+    int* __restrict__ kpNbrOff, DevCounters* __restrict__ ctr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* s_list = (unsigned*)smem_raw;  // [8 warps][MARK_WCAP]: every warp lists what it finds, no atomics
+  __shared__ int s_wcnt[8];
+  __shared__ long long s_off;
   const int total = kpOff[n_scans];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned* mylist = s_list + w * MARK_WCAP;
   for (int g = blockIdx.x; g < total; g += gridDim.x) {
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     const float4 o = kpOut[g];
     const int s = kpScan[g];
-    int cnt = 0;
+    int wcnt = 0;
     if (finite3(o.x, o.y, o.z)) {
       const long long base = scan_off[s];
       const float4* so = sorted + base;
@@ -1418,20 +1428,59 @@ __global__ void __launch_bounds__(256) k_desc_mark(
       for (int r = cy0 + w; r <= cy1; r += 8) {
         int b, e;
         row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
-        for (int i = b + lane; i < e; i += 32) {
-          const float4 q = so[i];
-          const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
-          if (d2 < P.R2f) { cnt++; rho[base + i] = -(s + 1); }
+        for (int i0 = b; i0 < e; i0 += 32) {
+          const int i = i0 + lane;
+          bool isn = false;
+          if (i < e) {
+            const float4 q = so[i];
+            isn = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z) < P.R2f;
+            if (isn) rho[base + i] = -(s + 1);
+          }
+          const unsigned m = __ballot_sync(FE_FULL, isn);
+          const int pos = wcnt + __popc(m & lanemask_lt());
+          if (isn && pos < MARK_WCAP) mylist[pos] = (unsigned)i;
+          wcnt += __popc(m);
         }
       }
     }
+    if (lane == 0) s_wcnt[w] = wcnt;
+    __syncthreads();
+    int n = 0, before = 0;
+    bool fits = true;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FE_FULL, cnt, d);
-    if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    for (int k = 0; k < 8; k++) {
+      const int c = s_wcnt[k];
+      if (k < w) before += c;
+      n += c;
+      fits = fits && (c <= MARK_WCAP);
+    }
+    if (threadIdx.x == 0) {
+      kpNbr[g] = n;
+      long long off = -1;
+      if (n > 0 && fits) {
+        off = (long long)atomicAdd(&ctr->nbr_cursor, (unsigned long long)n);
+        if (off + n > nbrCap) off = -1;
+      }
+      s_off = off;
+      kpNbrOff[g] = (int)off;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) kpNbr[g] = s_cnt;
-    __syncthreads();
+    const long long off = s_off;
+    if (off >= 0)
+      for (int t = lane; t < wcnt; t += 32) nbrPool[off + before + t] = mylist[t];
   }
+}
+
+// Position of every keypoint among the keypoints of its scan that have neighbours: the index of its
+// RNG draws (3dsc.hpp consumes three per keypoint that reaches the axis computation).
+__global__ void __launch_bounds__(256) k_kp_rank(const int* __restrict__ kpScan, const int* __restrict__ kpOff, int n_scans,
+                                                 const int* __restrict__ kpNbr, int* __restrict__ kpRank) {
+  const int total = kpOff[n_scans];
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int c = 0;
+  for (int j = kpOff[kpScan[g]]; j < g; j++) c += (kpNbr[j] > 0) ? 1 : 0;
+  kpRank[g] = c;
 }
 
 // ============================================================================================
@@ -1553,6 +1602,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted, SurfIndex X,
     const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
     const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
+    const unsigned* __restrict__ nbrPool, const int* __restrict__ kpNbrOff, const int* __restrict__ kpRank,
     float* __restrict__ desc, DevCounters* __restrict__ ctr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keyA = (unsigned long long*)smem_raw;
@@ -1562,7 +1612,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
   float* hist = wB + CAP;
   int* binCnt = (int*)hist;  // the histogram's storage counts records per bin while they are collected
   unsigned* nbrList = (unsigned*)keyB;  // compacted neighbour positions (consumed before keyB is written)
-  __shared__ int s_rank, s_cnt, s_total;
+  __shared__ int s_cnt, s_total;
   __shared__ int s_scan[40];
   __shared__ int s_spanB[32], s_spanS[33];
   const int total = kpOff[n_scans];
@@ -1578,19 +1628,14 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     }
     const bool ordered = nb <= CAP;
     const int s = kpScan[g];
+    // the RNG is consumed only by keypoints that have neighbours, in keypoint order (k_kp_rank)
+    const int rank = kpRank[g];
+    const int off = ordered ? kpNbrOff[g] : -1;  // >= 0: K4b left the neighbour list in nbrPool
+    const float4 o = kpOut[g];
+    const long long base = scan_off[s];
     for (int i = tid; i < FE_DESC_LEN; i += NT) hist[i] = 0.0f;
-    if (tid == 0) { s_rank = 0; s_cnt = 0; if (!ordered) atomicAdd(&ctr->desc_unordered, 1); }
+    if (tid == 0) { s_cnt = 0; if (!ordered) atomicAdd(&ctr->desc_unordered, 1); }
     __syncthreads();
-    // the RNG is consumed only by keypoints that have neighbours, in keypoint order
-    {
-      int c = 0;
-      for (int j = kpOff[s] + tid; j < g; j += NT) c += (kpNbr[j] > 0) ? 1 : 0;
-#pragma unroll
-      for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FE_FULL, c, d);
-      if (lane == 0 && c) atomicAdd(&s_rank, c);
-    }
-    __syncthreads();
-    const int rank = s_rank;
     if (rank >= axesCap) {
       if (tid == 0) atomicOr(&ctr->err, ERR_AXIS_CAP);
       for (int i = tid; i < FE_DESC_LEN; i += NT) out[i] = __int_as_float(0x7fc00000);
@@ -1598,8 +1643,6 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
       continue;
     }
     const float2 ax = axes[rank];  // normalised x_axis = (ax.x, ax.y, -0)
-    const float4 o = kpOut[g];
-    const long long base = scan_off[s];
     const float4* so = sorted + base;
     const unsigned* sk = X.sortedKey + base;
     const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
@@ -1607,7 +1650,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const int* rh = rho + base;
     const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
-    for (int r0 = cy0; r0 <= cy1; r0 += 32) {  // at most ~12 rows: one pass
+    for (int r0 = cy0; off < 0 && r0 <= cy1; r0 += 32) {  // at most ~12 rows: one pass
       if (w == 0) {
         int b = 0, e = 0;
         if (r0 + lane <= cy1) row_span(sk, rs, ct, P.sg_nx, r0 + lane, cx0, cx1, P.sg_bx, b, e);
@@ -1652,13 +1695,13 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
       __syncthreads();
     }
     if (ordered) {
-      const int nl = s_cnt;  // == nb
+      const int nl = (off >= 0) ? nb : s_cnt;  // == nb
       __syncthreads();
       if (tid == 0) s_cnt = 0;
       __syncthreads();
       // dense pass over the neighbours: bin, weight, record
       for (int t = tid; t < nl; t += NT) {
-        const int i = (int)nbrList[t];
+        const int i = (off >= 0) ? (int)nbrPool[off + t] : (int)nbrList[t];
         const float4 q = so[i];
         const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
         int bin; float wgt;
