@@ -85,6 +85,8 @@ struct DevCounters {
   int ovf_merge2;      // scans deferred from the large K3 to the global-memory instantiation
   int pad[1];
   unsigned long long nbr_cursor;  // neighbour-list pool (K4b -> K4d)
+  int kd_cursor;                  // next keypoint batch of the fast K4d instantiation
+  int pad2;
 };
 
 // getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
@@ -1525,6 +1527,7 @@ __device__ __forceinline__ float eigen_sum3(float a0, float a1, float a2) {
   return __fadd_rn(a0, __fadd_rn(a1, a2));  // Eigen's unrolled 3-term reduction: a0 + (a1 + a2)
 }
 
+constexpr int KD_BATCH = 4;   // keypoints a block of the fast instantiation takes per request
 constexpr int DCAP = 1536;    // contributions per keypoint of the fast instantiation (256 threads, 5 blocks / SM)
 constexpr int DCAP_M = 4096;  // of the medium instantiation (512 threads, 2 blocks / SM)
 constexpr int DCAP_L = 8192;  // of the large instantiation (512 threads, 1 block / SM)
@@ -1617,7 +1620,23 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
   __shared__ int s_spanB[32], s_spanS[33];
   const int total = kpOff[n_scans];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int g = blockIdx.x; g < total; g += gridDim.x) {
+  // The fast instantiation takes the keypoints in batches of KD_BATCH from a device-wide cursor (their
+  // cost varies with the neighbour count; equal static shares left the slowest block ~40 % behind);
+  // the next batch is requested before the current one is worked on.  The larger instantiations
+  // mostly skip, and stride statically.
+  constexpr bool DYN = (NB_MIN == 0);
+  __shared__ int s_next;
+  int g0 = blockIdx.x, gstep = gridDim.x, glen = 1;
+  if (DYN) {
+    if (tid == 0) s_next = atomicAdd(&ctr->kd_cursor, KD_BATCH);
+    __syncthreads();
+    g0 = s_next; glen = KD_BATCH;
+  }
+  while (g0 < total) {
+  int nxt = 0;
+  if (DYN && tid == 0) nxt = atomicAdd(&ctr->kd_cursor, KD_BATCH);
+  const int gend = min(g0 + glen, total);
+  for (int g = g0; g < gend; g++) {
     float* out = desc + (long long)g * FE_DESC_LEN;
     const int nb = kpNbr[g];
     if (NB_MIN > 0 && nb <= NB_MIN) continue;  // a smaller instantiation's keypoint
@@ -1770,6 +1789,15 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     }
     for (int i = tid; i < FE_DESC_LEN; i += NT) out[i] = hist[i];
     __syncthreads();
+  }
+  if (DYN) {
+    __syncthreads();
+    if (tid == 0) s_next = nxt;
+    __syncthreads();
+    g0 = s_next;
+  } else {
+    g0 += gstep;
+  }
   }
 }
 
