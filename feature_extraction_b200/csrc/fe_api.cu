@@ -35,6 +35,7 @@ struct Slot {
   int *d_kfBase = nullptr, *d_kfCnt = nullptr, *d_kcBase = nullptr, *d_kcCnt = nullptr;
   int *d_kpBase = nullptr, *d_kpCnt = nullptr, *d_kpOff = nullptr, *d_kpScan = nullptr, *d_kpNbr = nullptr;
   int *d_kpNbrOff = nullptr, *d_kpRank = nullptr;  // K4b -> K4d: slice of the neighbour pool (d_keyA), RNG rank
+  int *d_kpListM = nullptr, *d_kpListL = nullptr;  // keypoints of K4d's medium / large instantiation
   int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
   unsigned short* d_cellTab = nullptr;
   int* d_tabOk = nullptr;
@@ -222,7 +223,7 @@ cudaError_t halloc(T** p, size_t n) { return cudaHostAlloc((void**)p, std::max<s
 void free_slot(Slot& s) {
   void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
-                s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_rowStart,
+                s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
                 s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
@@ -265,6 +266,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_kpBase, ns)); CK(dalloc(&s.d_kpCnt, ns)); CK(dalloc(&s.d_kpOff, ns + 1));
   CK(dalloc(&s.d_kpScan, (size_t)s.capKp)); CK(dalloc(&s.d_kpNbr, (size_t)s.capKp));
   CK(dalloc(&s.d_kpNbrOff, (size_t)s.capKp)); CK(dalloc(&s.d_kpRank, (size_t)s.capKp));
+  CK(dalloc(&s.d_kpListM, (size_t)s.capKp)); CK(dalloc(&s.d_kpListL, (size_t)s.capKp));
   CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1)); CK(dalloc(&s.d_tabOk, ns));
   CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfRings2, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfMerge2, ns));
   CK(dalloc(&s.d_ovfSurf, ns));
@@ -391,14 +393,20 @@ int set_kernel_attrs(fe_ctx* ctx) {
 // K4d: three instantiations split the keypoints by neighbour count (smaller footprint = more blocks / SM)
 void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp) {
 #define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, \
-                     s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, s.d_desc, s.d_ctr
+                     s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, FE_DESC_LIST, s.d_desc, s.d_ctr
   // the blocks stride over the keypoints with equal shares: grids of exactly one resident wave
   static int perSm = 0;
   if (!perSm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_desc_hist<256, DCAP, 0, false>, 256,
                                                               desc_smem_bytes(DCAP, 256)) != cudaSuccess) perSm = 4;
+#define FE_DESC_LIST nullptr, nullptr
   k_desc_hist<256, DCAP, 0, false><<<std::min(gridKp, 148 * std::max(perSm, 1)), 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
+#undef FE_DESC_LIST
+#define FE_DESC_LIST s.d_kpListM, &s.d_ctr->n_list_m
   k_desc_hist<512, DCAP_M, DCAP, false><<<std::min(gridKp, 148 * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
+#undef FE_DESC_LIST
+#define FE_DESC_LIST s.d_kpListL, &s.d_ctr->n_list_l
   k_desc_hist<512, DCAP_L, DCAP_M, true><<<std::min(gridKp, 148), 512, desc_smem_bytes(DCAP_L, 512), s.stream>>>(FE_DESC_ARGS);
+#undef FE_DESC_LIST
 #undef FE_DESC_ARGS
   ctx->launches += 3;
 }
@@ -413,7 +421,7 @@ void launch_desc_mark(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
   k_desc_mark<<<gridKp, 256, MARK_LCAP * sizeof(unsigned), s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted,
                                                                        surf_index(ctx, s), s.d_scan_off, P, s.d_rho, s.d_kpNbr,
                                                                        s.d_keyA, nbrCap, s.d_kpNbrOff, s.d_ctr);
-  k_kp_rank<<<(int)((s.capKp + 255) / 256), 256, 0, s.stream>>>(s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_kpRank);
+  k_kp_rank<<<(int)((s.capKp + 255) / 256), 256, 0, s.stream>>>(s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_ctr);
   ctx->launches += 2;
 }
 

@@ -86,6 +86,7 @@ struct DevCounters {
   int pad[1];
   unsigned long long nbr_cursor;  // neighbour-list pool (K4b -> K4d)
   int kd_cursor;                  // next keypoint batch of the fast K4d instantiation
+  int n_list_m, n_list_l;         // keypoints listed for the medium / large K4d instantiation
   int pad2;
 };
 
@@ -1400,6 +1401,10 @@ __device__ __forceinline__ void row_span(const unsigned* __restrict__ sk, const 
 // MARK_WCAP or the pool is full — K4d then finds the neighbours itself).
 // rho[i] = -(scan+1) marks "density needed".  One block per keypoint, grid-stride.
 // ============================================================================================
+constexpr int KD_BATCH = 4;   // keypoints a block of the fast K4d instantiation takes per request
+constexpr int DCAP = 1536;    // K4d: contributions per keypoint of the fast instantiation (256 threads, 5 blocks / SM)
+constexpr int DCAP_M = 4096;  // of the medium instantiation (512 threads, 2 blocks / SM)
+constexpr int DCAP_L = 8192;  // of the large instantiation (512 threads, 1 block / SM)
 constexpr int MARK_WCAP = 512;            // list entries per warp (16 KB per block: 8 blocks / SM stay resident)
 constexpr int MARK_LCAP = 8 * MARK_WCAP;  // longer lists: K4d's larger instantiations find the neighbours themselves
 
@@ -1476,13 +1481,18 @@ __global__ void __launch_bounds__(256) k_desc_mark(
 // Position of every keypoint among the keypoints of its scan that have neighbours: the index of its
 // RNG draws (3dsc.hpp consumes three per keypoint that reaches the axis computation).
 __global__ void __launch_bounds__(256) k_kp_rank(const int* __restrict__ kpScan, const int* __restrict__ kpOff, int n_scans,
-                                                 const int* __restrict__ kpNbr, int* __restrict__ kpRank) {
+                                                 const int* __restrict__ kpNbr, int* __restrict__ kpRank,
+                                                 int* __restrict__ listM, int* __restrict__ listL, DevCounters* __restrict__ ctr) {
   const int total = kpOff[n_scans];
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
   int c = 0;
   for (int j = kpOff[kpScan[g]]; j < g; j++) c += (kpNbr[j] > 0) ? 1 : 0;
   kpRank[g] = c;
+  // the few keypoints of K4d's larger instantiations, listed so that those do not have to look for them
+  const int nb = kpNbr[g];
+  if (nb > DCAP_M) listL[atomicAdd(&ctr->n_list_l, 1)] = g;
+  else if (nb > DCAP) listM[atomicAdd(&ctr->n_list_m, 1)] = g;
 }
 
 // ============================================================================================
@@ -1527,10 +1537,6 @@ __device__ __forceinline__ float eigen_sum3(float a0, float a1, float a2) {
   return __fadd_rn(a0, __fadd_rn(a1, a2));  // Eigen's unrolled 3-term reduction: a0 + (a1 + a2)
 }
 
-constexpr int KD_BATCH = 4;   // keypoints a block of the fast instantiation takes per request
-constexpr int DCAP = 1536;    // contributions per keypoint of the fast instantiation (256 threads, 5 blocks / SM)
-constexpr int DCAP_M = 4096;  // of the medium instantiation (512 threads, 2 blocks / SM)
-constexpr int DCAP_L = 8192;  // of the large instantiation (512 threads, 1 block / SM)
 constexpr size_t desc_smem_bytes(int cap, int nt) {
   return (size_t)cap * 24 + FE_DESC_LEN * 4 + 64 + 0 * nt;
 }
@@ -1606,7 +1612,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
     const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
     const unsigned* __restrict__ nbrPool, const int* __restrict__ kpNbrOff, const int* __restrict__ kpRank,
-    float* __restrict__ desc, DevCounters* __restrict__ ctr) {
+    const int* __restrict__ glist, const int* __restrict__ nlist, float* __restrict__ desc, DevCounters* __restrict__ ctr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keyA = (unsigned long long*)smem_raw;
   unsigned long long* keyB = keyA + CAP;
@@ -1623,7 +1629,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
   // The fast instantiation takes the keypoints in batches of KD_BATCH from a device-wide cursor (their
   // cost varies with the neighbour count; equal static shares left the slowest block ~40 % behind);
   // the next batch is requested before the current one is worked on.  The larger instantiations
-  // mostly skip, and stride statically.
+  // stride over the list of their keypoints that k_kp_rank made.
   constexpr bool DYN = (NB_MIN == 0);
   __shared__ int s_next;
   int g0 = blockIdx.x, gstep = gridDim.x, glen = 1;
@@ -1632,11 +1638,13 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     __syncthreads();
     g0 = s_next; glen = KD_BATCH;
   }
-  while (g0 < total) {
+  const int bound = DYN ? total : *nlist;
+  while (g0 < bound) {
   int nxt = 0;
   if (DYN && tid == 0) nxt = atomicAdd(&ctr->kd_cursor, KD_BATCH);
-  const int gend = min(g0 + glen, total);
-  for (int g = g0; g < gend; g++) {
+  const int gend = min(g0 + glen, bound);
+  for (int gi = g0; gi < gend; gi++) {
+    const int g = DYN ? gi : glist[gi];
     float* out = desc + (long long)g * FE_DESC_LEN;
     const int nb = kpNbr[g];
     if (NB_MIN > 0 && nb <= NB_MIN) continue;  // a smaller instantiation's keypoint
