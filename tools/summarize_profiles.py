@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGE_OF = [("k_level_crop_ring", "K1 level+crop+ring"), ("k_cluster_rings", "K2 ring clusters"),
-            ("k_merge_keypoints", "K3 merge keypoints"), ("k_kp_", "keypoint CSR"),
+            ("k_merge_keypoints", "K3 merge keypoints"), ("k_kp_rank", "K4b mark neighbours"), ("k_kp_", "keypoint CSR"),
             ("k_surface_grid", "K4a surface grid"), ("k_desc_mark", "K4b mark neighbours"),
             ("k_density", "K4c density"), ("k_desc_hist", "K4d shape context")]
 
