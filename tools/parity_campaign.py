@@ -7,11 +7,12 @@ from oracle import oracle_binding as ob
 from feature_extraction_b200 import FeatureExtractionNode, synth
 from util import to_fe_params
 
+SHIFT = int(sys.argv[1]) if len(sys.argv) > 1 else 0  # other scan indices = other seeded scenes
 rows = []
 for cfg, nsc, base in ((1, 400, 5000), (2, 4000, 50000), (3, 160, 7000), (4, 240, 9000)):
     P = ob.launch_playback() if cfg == 1 else ob.node_default()
     if cfg == 4: P.descriptor_radius = 5.0
-    pts, offs, rp = synth.generate(cfg, nsc, scan_index_base=base)
+    pts, offs, rp = synth.generate(cfg, nsc, scan_index_base=base + SHIFT)
     nd = FeatureExtractionNode(to_fe_params(P), max_points=int(offs[-1]) + 4096, max_scans=nsc, max_keypoints=max(4096, nsc * 64))
     t = time.time(); ko, kp, d = nd.processBatch(pts, offs, rp); tg = time.time() - t
     t = time.time(); ko_o, kp_o, d_o, m_o = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=len(os.sched_getaffinity(0)), want_margin=True); tc = time.time() - t
@@ -30,5 +31,5 @@ out = ["# Parity campaign (GPU C-ABI vs CPU oracle, KD-tree mode), round 1", "",
        "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 for r in rows:
     out.append("| %d | %d | %d | %d | %s | %s | %d | %d | %.3g | %d | %.3g | %.3f | %.2f |" % r)
-open(os.path.join(ROOT, "gpurun_out", "parity_campaign.md"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "gpurun_out", "parity_campaign%s.md" % ("_%d" % SHIFT if SHIFT else "")), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
