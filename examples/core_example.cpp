@@ -47,8 +47,18 @@ int main() {
     const bool same = keypoints.size() == kp2.size() &&
                       (keypoints.empty() || std::memcmp(keypoints.data(), kp2.data(), keypoints.size() * sizeof(Point)) == 0);
     for (size_t i = 0; i < kp2.size(); i++) std::printf("  kp %zu: %.4f %.4f %.4f el %.2f\n", i, kp2[i].x, kp2[i].y, kp2[i].z, kp2[i].intensity);
-    std::printf("%s\n", same ? "identical" : "DIFFERENT");
-    return same ? 0 : 1;
+    // the ~features records (src:119) straight from the device against the host-side packing
+    PointCloud kp3;
+    std::vector<float> records, packed(kp2.size() * (size_t)FE_RECORD_FLOATS);
+    node.processScanRecords(cloud_full, kp3, records);
+    bool recSame = true;
+    if (node.descriptorEstimation) {
+      fe_pack_point_descriptors(kp2.data(), d2.data(), (int64_t)kp2.size(), packed.data());
+      recSame = records.size() == packed.size() &&
+                (packed.empty() || std::memcmp(records.data(), packed.data(), packed.size() * sizeof(float)) == 0);
+    }
+    std::printf("%s\n", (same && recSame) ? "identical" : "DIFFERENT");
+    return (same && recSame) ? 0 : 1;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());
     return 2;

@@ -78,6 +78,7 @@ struct fe_ctx {
   float2* d_axes = nullptr;
   int axesCap = 0;
   bool cloudOutputs = false;
+  bool recordOutput = false;  // descriptors leave as FE_RECORD_FLOATS-float PointDescriptor records
   // results (host, pinned, grown on demand)
   std::vector<int64_t> kpOffsets;
   fe_point_t* h_kp = nullptr;
@@ -272,7 +273,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_ovfSurf, ns));
   CK(dalloc(&s.d_slabs, (size_t)NGLOBAL * cluster_slab_bytes(ECAP_G)));
   CK(dalloc(&s.d_kfPool, (size_t)s.capKf)); CK(dalloc(&s.d_kpPool, (size_t)s.capKp)); CK(dalloc(&s.d_kpOut, (size_t)s.capKp));
-  CK(dalloc(&s.d_desc, (size_t)s.capKp * FE_DESC_LEN));
+  CK(dalloc(&s.d_desc, (size_t)s.capKp * FE_RECORD_FLOATS));  // room for either output layout
   CK(dalloc(&s.d_ctr, 1));
   CK(halloc(&s.h_scan_off, ns + 1)); CK(halloc(&s.h_chunk_off, ns + 1)); CK(halloc(&s.h_rot, ns * 9));
   CK(halloc(&s.h_ctr, 1)); CK(halloc(&s.h_kpOff, ns + 1)); CK(halloc(&s.h_perScan, ns + 1));
@@ -391,9 +392,10 @@ int set_kernel_attrs(fe_ctx* ctx) {
 }
 
 // K4d: three instantiations split the keypoints by neighbour count (smaller footprint = more blocks / SM)
-void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp) {
+void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp, bool records) {
+  const int descStride = records ? FE_RECORD_FLOATS : FE_DESC_LEN, descOff = records ? 5 : 0;
 #define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, \
-                     s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, FE_DESC_LIST, s.d_desc, s.d_ctr
+                     s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, FE_DESC_LIST, s.d_desc, descStride, descOff, s.d_ctr
   // the blocks stride over the keypoints with equal shares: grids of exactly one resident wave
   static int perSm = 0;
   if (!perSm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_desc_hist<256, DCAP, 0, false>, 256,
@@ -409,6 +411,10 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
 #undef FE_DESC_LIST
 #undef FE_DESC_ARGS
   ctx->launches += 3;
+  if (records) {
+    k_record_frame<<<148 * 2, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpOff, nscans, s.d_desc, descStride, FE_DESC_LEN);
+    ctx->launches++;
+  }
 }
 
 // K4b: mark + count + neighbour lists (the pool is d_keyA, idle once K4a is done), then the RNG ranks.
@@ -524,7 +530,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
       ctx->launches++;
     }
     mark(ctx, s, "K4c density");
-    launch_desc_hist(ctx, s, nscans, P, gridKp);
+    launch_desc_hist(ctx, s, nscans, P, gridKp, ctx->recordOutput);
     mark(ctx, s, "K4d shape context");
   }
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
@@ -559,8 +565,8 @@ int grow_results(fe_ctx* ctx, int64_t needKp, bool desc) {
   if (desc && ctx->capResKp > ctx->capResDesc) {
     for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
     float* nd = nullptr;
-    CK(halloc(&nd, (size_t)ctx->capResKp * FE_DESC_LEN));
-    if (ctx->h_desc) { memcpy(nd, ctx->h_desc, (size_t)ctx->capResDesc * FE_DESC_LEN * sizeof(float)); cudaFreeHost(ctx->h_desc); }
+    CK(halloc(&nd, (size_t)ctx->capResKp * FE_RECORD_FLOATS));
+    if (ctx->h_desc) { memcpy(nd, ctx->h_desc, (size_t)ctx->capResDesc * FE_RECORD_FLOATS * sizeof(float)); cudaFreeHost(ctx->h_desc); }
     ctx->h_desc = nd;
     ctx->capResDesc = ctx->capResKp;
   }
@@ -579,7 +585,8 @@ int finalize_subbatch(fe_ctx* ctx, Slot& s, int64_t& kpRun, bool desc) {
   for (int i = 0; i <= s.nscans; i++) ctx->kpOffsets[s.firstScan + i] = kpRun + s.h_kpOff[i];
   if (K > 0) {
     CK(cudaMemcpyAsync(ctx->h_kp + kpRun, s.d_kpOut, (size_t)K * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
-    if (desc) CK(cudaMemcpyAsync(ctx->h_desc + kpRun * FE_DESC_LEN, s.d_desc, (size_t)K * FE_DESC_LEN * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    const size_t dl = ctx->recordOutput ? FE_RECORD_FLOATS : FE_DESC_LEN;
+    if (desc) CK(cudaMemcpyAsync(ctx->h_desc + kpRun * dl, s.d_desc, (size_t)K * dl * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
   }
   kpRun += K;
   return FE_OK;
@@ -724,6 +731,13 @@ void fe_destroy(fe_ctx_t* ctx) {
 int fe_enable_cloud_outputs(fe_ctx_t* ctx, int32_t enable) {
   if (!ctx) return FE_ERR_INVALID;
   ctx->cloudOutputs = enable != 0;
+  return FE_OK;
+}
+
+int fe_enable_record_output(fe_ctx_t* ctx, int32_t enable) {
+  if (!ctx) return FE_ERR_INVALID;
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+  ctx->recordOutput = enable != 0;
   return FE_OK;
 }
 
@@ -1187,7 +1201,7 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
                                                                                (long long)n, s.d_rho);
     ctx->launches++;
   }
-  launch_desc_hist(ctx, s, 1, P, 148 * 4);
+  launch_desc_hist(ctx, s, 1, P, 148 * 4, false);
   ctx->dp = saved;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, q));
@@ -1236,6 +1250,15 @@ int fe_multi_create(const int32_t* devices, int32_t n_devices, const fe_params_t
   return FE_OK;
 }
 
+int fe_multi_enable_record_output(fe_multi_t* m, int32_t enable) {
+  if (!m) return FE_ERR_INVALID;
+  for (fe_ctx_t* c : m->ctx) {
+    const int st = fe_enable_record_output(c, enable);
+    if (st) return st;
+  }
+  return FE_OK;
+}
+
 void fe_multi_destroy(fe_multi_t* m) {
   if (!m) return;
   for (fe_ctx_t* c : m->ctx) fe_destroy(c);
@@ -1274,6 +1297,7 @@ int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_
   for (int g = 0; g < G; g++) kbase[g + 1] = kbase[g] + res[g].n_keypoints;
   const int64_t K = kbase[G];
   const bool desc = m->ctx[0]->params.estimate_descriptors != 0;
+  const size_t dl = m->ctx[0]->recordOutput ? FE_RECORD_FLOATS : FE_DESC_LEN;
   m->kpOffsets.assign((size_t)n_scans + 1, 0);
   if (K > m->capKp) {
     free(m->kp);
@@ -1284,7 +1308,7 @@ int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_
   if (desc && K > m->capDesc) {
     free(m->desc);
     m->capDesc = K + K / 2 + 1024;
-    m->desc = (float*)malloc((size_t)m->capDesc * FE_DESC_LEN * sizeof(float));
+    m->desc = (float*)malloc((size_t)m->capDesc * FE_RECORD_FLOATS * sizeof(float));
     if (!m->desc) { m->capDesc = 0; m->err = "out of host memory"; return FE_ERR_CAPACITY; }
   }
   {
@@ -1295,7 +1319,7 @@ int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_
         for (int i = 0; i <= ns; i++) m->kpOffsets[lo[g] + i] = kbase[g] + res[g].keypoint_offsets[i];
         if (res[g].n_keypoints > 0) {
           memcpy(m->kp + kbase[g], res[g].keypoints, (size_t)res[g].n_keypoints * sizeof(fe_point_t));
-          if (desc) memcpy(m->desc + kbase[g] * FE_DESC_LEN, res[g].descriptors, (size_t)res[g].n_keypoints * FE_DESC_LEN * sizeof(float));
+          if (desc) memcpy(m->desc + kbase[g] * dl, res[g].descriptors, (size_t)res[g].n_keypoints * dl * sizeof(float));
         }
       });
     for (auto& t : th) t.join();

@@ -1612,7 +1612,8 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
     const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
     const unsigned* __restrict__ nbrPool, const int* __restrict__ kpNbrOff, const int* __restrict__ kpRank,
-    const int* __restrict__ glist, const int* __restrict__ nlist, float* __restrict__ desc, DevCounters* __restrict__ ctr) {
+    const int* __restrict__ glist, const int* __restrict__ nlist, float* __restrict__ desc, int descStride, int descOff,
+    DevCounters* __restrict__ ctr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keyA = (unsigned long long*)smem_raw;
   unsigned long long* keyB = keyA + CAP;
@@ -1645,7 +1646,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
   const int gend = min(g0 + glen, bound);
   for (int gi = g0; gi < gend; gi++) {
     const int g = DYN ? gi : glist[gi];
-    float* out = desc + (long long)g * FE_DESC_LEN;
+    float* out = desc + (long long)g * descStride + descOff;
     const int nb = kpNbr[g];
     if (NB_MIN > 0 && nb <= NB_MIN) continue;  // a smaller instantiation's keypoint
     if (!LAST && nb > CAP) continue;           // a larger instantiation's keypoint
@@ -1806,6 +1807,24 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
   } else {
     g0 += gstep;
   }
+  }
+}
+
+// Record output (fe_enable_record_output): everything of a pcl::PointDescriptor record
+// (feature_extraction_node.h:35-53, filled by pcl::concatenateFields at src:119) that is not the
+// descriptor itself — x, y, z, the unregistered pad float, intensity, rf[9] = 0, tail padding.
+__global__ void __launch_bounds__(256) k_record_frame(const float4* __restrict__ kpOut, const int* __restrict__ kpOff, int n_scans,
+                                                      float* __restrict__ rec, int stride, int descLen) {
+  const int total = kpOff[n_scans];
+  const int tail = stride - 5 - descLen;  // rf[9] + alignment padding
+  const int per = 5 + tail;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)total * per;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t / per), f = (int)(t % per);
+    const float4 k = kpOut[g];
+    float* r = rec + (long long)g * stride;
+    if (f < 5) r[f] = (f == 0) ? k.x : (f == 1) ? k.y : (f == 2) ? k.z : (f == 3) ? 0.0f : k.w;
+    else r[5 + descLen + (f - 5)] = 0.0f;
   }
 }
 

@@ -12,6 +12,7 @@ import numpy as np
 from . import _native as N
 
 DESC_LEN = N.DESC_LEN
+RECORD_FLOATS = N.RECORD_FLOATS
 
 
 class FeatureExtractionError(RuntimeError):
@@ -77,6 +78,9 @@ class FeatureExtractionNode:
     Members mirror feature_extraction_node.h:115-127 (through `params`); `roll`/`pitch` are the
     state imuCallback leaves (src:63-65).  Not thread-safe, like the reference (ros::spin).
     """
+
+    record_output = False  # see enableRecordOutput
+
 
     def __init__(self, params=None, device=0, max_points=0, max_scans=0, max_keypoints=0, max_ring_clusters=0):
         self._ctx = C.c_void_p()
@@ -229,11 +233,19 @@ class FeatureExtractionNode:
             kp = np.ctypeslib.as_array(C.cast(res.keypoints, C.POINTER(C.c_float)), shape=(K, 4))
         if self.params.estimate_descriptors:
             d = np.zeros((0, DESC_LEN), np.float32)
+            dl = RECORD_FLOATS if self.record_output else DESC_LEN
+            d = np.zeros((0, dl), np.float32)
             if K > 0 and res.descriptors:
-                d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, DESC_LEN))
+                d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, dl))
         if copy:
             return ko.copy(), kp.copy(), (d.copy() if d is not None else None)
         return ko, kp, d
+
+    def enableRecordOutput(self, enable=True):
+        """fe_enable_record_output: descriptors leave the device as (K, 1996) pcl::PointDescriptor
+        records (concatenateFields, src:119) instead of (K, 1980) bins."""
+        self._check(N.lib().fe_enable_record_output(self._ctx, 1 if enable else 0))
+        self.record_output = bool(enable)
 
     def processBatchDevice(self, d_points_ptr, scan_offsets, roll_pitch):
         """fe_process_batch_device: points already in HBM (raw device pointer); results stay there.
@@ -300,6 +312,9 @@ class MultiGpuExtractor:
     """fe_multi_*: scans sharded over several GPUs of one box in ONE process (a host thread and a
     context per GPU, contiguous scan ranges, host-side CSR gather; no collective)."""
 
+    record_output = False
+
+
     def __init__(self, devices, params=None, max_points=0, max_scans=0, max_keypoints=0, max_ring_clusters=0):
         self._m = C.c_void_p()
         self.params = (params or node_default()).copy()
@@ -309,6 +324,12 @@ class MultiGpuExtractor:
         if st != N.FE_OK:
             self._m = C.c_void_p()
             raise FeatureExtractionError(st, "fe_multi_create failed")
+
+    def enableRecordOutput(self, enable=True):
+        st = N.lib().fe_multi_enable_record_output(self._m, 1 if enable else 0)
+        if st != N.FE_OK:
+            raise FeatureExtractionError(st, "fe_multi_enable_record_output")
+        self.record_output = bool(enable)
 
     def close(self):
         if self._m:
@@ -333,11 +354,12 @@ class MultiGpuExtractor:
         K = int(res.n_keypoints)
         ko = np.ctypeslib.as_array(res.keypoint_offsets, shape=(B + 1,)).copy()
         kp = np.zeros((0, 4), np.float32)
-        d = np.zeros((0, DESC_LEN), np.float32) if self.params.estimate_descriptors else None
+        dl = RECORD_FLOATS if self.record_output else DESC_LEN
+        d = np.zeros((0, dl), np.float32) if self.params.estimate_descriptors else None
         if K > 0:
             kp = np.ctypeslib.as_array(C.cast(res.keypoints, C.POINTER(C.c_float)), shape=(K, 4))
             if res.descriptors:
-                d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, DESC_LEN))
+                d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, dl))
             if copy:
                 kp = kp.copy()
                 d = d.copy() if d is not None else None

@@ -155,6 +155,16 @@ int fe_enable_cloud_outputs(fe_ctx_t* ctx, int32_t enable);
 int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_point_t** cloud,
                          const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud);
 
+/* Record output — pcl::concatenateFields(*keypoints, *descriptors, *pt_descriptors) at src:119 done
+ * on the device: when enabled, `descriptors` of every following result (fe_process_batch,
+ * fe_process_batch_layout, fe_process_batch_device, fe_multi_process_batch) points to n_keypoints
+ * records of FE_RECORD_FLOATS floats in the layout of pcl::PointDescriptor
+ * (feature_extraction_node.h:35-53): x, y, z, 0 | intensity | descriptor[1980] | rf[9] = 0 | padding —
+ * what fe_pack_point_descriptors() would build on the host, ready to be published as ~features.
+ * `keypoints` is filled as before.  Needs estimate_descriptors != 0. */
+int fe_enable_record_output(fe_ctx_t* ctx, int32_t enable);
+int fe_multi_enable_record_output(fe_multi_t* m, int32_t enable);
+
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of
  * fe_process_batch_device is launched on): begin, run any number of calls, end -> elapsed ms. */
 int fe_timer_begin(fe_ctx_t* ctx);

@@ -123,6 +123,22 @@ class FeatureExtractionCore {
     if (r.descriptors) descriptors.assign(r.descriptors, r.descriptors + r.n_keypoints * FE_DESC_LEN);
   }
 
+  // As processScan, but the ~features message body leaves the device finished: one
+  // FE_RECORD_FLOATS-float pcl::PointDescriptor record per keypoint (concatenateFields, src:119).
+  void processScanRecords(const PointCloud& cloud_full, PointCloud& keypoints, std::vector<float>& pt_descriptors) {
+    sync();
+    check(fe_enable_record_output(ctx_, 1), "processScanRecords");
+    const int64_t offs[2] = {0, (int64_t)cloud_full.size()};
+    const double rp[2] = {roll, pitch};
+    fe_batch_result_t r;
+    const int st = fe_process_batch(ctx_, cloud_full.data(), offs, rp, 1, &r);
+    fe_enable_record_output(ctx_, 0);
+    check(st, "processScanRecords");
+    keypoints.assign(r.keypoints, r.keypoints + r.n_keypoints);
+    pt_descriptors.clear();
+    if (r.descriptors) pt_descriptors.assign(r.descriptors, r.descriptors + r.n_keypoints * FE_RECORD_FLOATS);
+  }
+
   fe_ctx_t* context() { return ctx_; }
 
  private:

@@ -196,3 +196,48 @@ def test_in_process_multi_gpu_sharding_equals_single_context(ob, synth, nodes):
         ko2, kp2, d2 = m.processBatch(pts, offs, rp)
         m.close()
         assert np.array_equal(ko, ko2) and bits_equal(kp, kp2) and bits_equal(d, d2)
+
+
+def test_record_output_equals_concatenate_fields_on_the_host(ob, synth, nodes):
+    """SURVEY.md §8(f)1, output side: with fe_enable_record_output the device emits the 7,984-byte
+    pcl::PointDescriptor records (feature_extraction_node.h:35-53, concatenateFields at src:119)
+    itself — host, device-resident and multi-GPU entry points; sub-batching must not matter."""
+    import torch
+    from feature_extraction_b200 import FeatureExtractionNode, MultiGpuExtractor, pack_point_descriptors
+    from feature_extraction_b200.node import RECORD_FLOATS
+    nd = nodes(2)
+    pts, offs, rp = synth.generate(2, 40, scan_index_base=2300)
+    pts = pts.copy()
+    pts[offs[7]:offs[8], 0] -= 500.0          # a scan without keypoints in the middle
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    want = pack_point_descriptors(kp, d)
+    assert want.shape == (len(kp), RECORD_FLOATS) and len(kp) > 40
+    P = to_fe_params(_params(ob, 2))
+    for max_scans in (64, 9):                 # one sub-batch / five sub-batches on two slots
+        r = FeatureExtractionNode(P, max_points=1 << 20, max_scans=max_scans, max_keypoints=4096)
+        r.enableRecordOutput(True)
+        ko2, kp2, rec = r.processBatch(pts, offs, rp)
+        assert np.array_equal(ko, ko2) and bits_equal(kp, kp2) and rec.shape == want.shape
+        assert bits_equal(rec, want)
+        if max_scans == 64:
+            dev = torch.from_numpy(pts).cuda()
+            torch.cuda.synchronize()
+            ko3, K, p_kp, p_rec = r.processBatchDevice(dev.data_ptr(), offs, rp)
+            assert K == len(kp) and bits_equal(r.download(p_rec, (K, RECORD_FLOATS)), want)
+            r.enableRecordOutput(False)       # back to plain bins on the same context
+            ko4, kp4, d4 = r.processBatch(pts, offs, rp)
+            assert d4.shape == d.shape and bits_equal(d4, d)
+        r.close()
+    m = MultiGpuExtractor([0, 0], P, max_points=1 << 20, max_scans=64, max_keypoints=4096)
+    m.enableRecordOutput(True)
+    ko5, kp5, rec5 = m.processBatch(pts, offs, rp)
+    m.close()
+    assert np.array_equal(ko, ko5) and bits_equal(rec5, want)
+    # descriptors off: no records, not an error
+    P0 = to_fe_params(_params(ob, 2))
+    P0.estimate_descriptors = 0
+    r = FeatureExtractionNode(P0, max_points=1 << 20, max_scans=64, max_keypoints=4096)
+    r.enableRecordOutput(True)
+    ko6, kp6, rec6 = r.processBatch(pts, offs, rp)
+    r.close()
+    assert rec6 is None and bits_equal(kp6, kp)
