@@ -1269,7 +1269,7 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     block_excl_scan<NTS>(v, &tot, sc);
     if (tid == 0) s_n = tot;
   }
-  for (int i = tid; i < nwords; i += NTS) cells[i] = 0u;
+  for (int i = tid; i < (nwords + 3) / 4; i += NTS) ((uint4*)cells)[i] = make_uint4(0u, 0u, 0u, 0u);  // 64 bytes of slack follow
   __syncthreads();
   const int n = s_n;
   if (n > 65535) {
@@ -1284,15 +1284,16 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     for (int i = tid; i <= ncells; i += NTS) tab[i] = 0;
     return;
   }
-  // (1) count: the survivors of a chunk are contiguous; every chunk is cut into 8 slices and the
-  //     slices are dealt to the warps (a scan has fewer chunks than the block has warps)
-  for (int it = w; it < nch * 8; it += NW) {
-    const int c = it >> 3, sl = it & 7;
-    const int cnt = surfCnt[c0 + c];
-    const int j1 = (cnt * (sl + 1)) >> 3;
+  // (1) count: the survivors of a chunk are contiguous; the chunks are cut into runs of 128 points that
+  //     are dealt to the warps (a scan has fewer chunks than the block has warps)
+  for (int it = w; it < nch * (CH / 128); it += NW) {
+    const int c = it / (CH / 128);
+    const int j1 = surfCnt[c0 + c];
     const float4* src = surf + base + (long long)c * CH;
     // four loads in flight per lane: the sweep is latency-bound, not bandwidth-bound
-    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 128) {
+    {
+      const int j = (it % (CH / 128)) * 128 + lane;
+      if (j - lane >= j1) continue;
       float4 q[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1338,25 +1339,23 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
   // (3) scatter: the start of a cell doubles as its cursor (it ends at the cell's end <= n <= 65535,
   //     so a 16-bit half never carries into its neighbour)
   float4* so = sorted + base;
-  unsigned* sk = sortedKey + base;
-  for (int it = w; it < nch * 8; it += NW) {
-    const int c = it >> 3, sl = it & 7;
-    const int cnt = surfCnt[c0 + c];
-    const int j1 = (cnt * (sl + 1)) >> 3;
+  for (int it = w; it < nch * (CH / 128); it += NW) {
+    const int c = it / (CH / 128);
+    const int j1 = surfCnt[c0 + c];
     const float4* src = surf + base + (long long)c * CH;
-    for (int j = ((cnt * sl) >> 3) + lane; j < j1; j += 128) {
+    {
+      const int j = (it % (CH / 128)) * 128 + lane;
+      if (j - lane >= j1) continue;
       float4 q[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (j + 32 * k < j1) {
-          const int cx = surf_cell(q[k].x, P.sx0, P.sg_inv, nx), cy = surf_cell(q[k].y, P.sy0, P.sg_inv, ny);
-          const int cell = cy * nx + cx;
+          const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
           const unsigned old = atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
           const int pos = (cell & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu);
-          so[pos] = q[k];
-          sk[pos] = ((unsigned)cy << P.sg_bx) | (unsigned)cx;
+          so[pos] = q[k];  // no sorted key: scans with a cell table are never searched by key
         }
       }
     }
