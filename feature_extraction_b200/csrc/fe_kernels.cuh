@@ -1286,23 +1286,21 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
   }
   // (1) count: the survivors of a chunk are contiguous; the chunks are cut into runs of 128 points that
   //     are dealt to the warps (a scan has fewer chunks than the block has warps)
-  for (int it = w; it < nch * (CH / 128); it += NW) {
-    const int c = it / (CH / 128);
+  for (int it = w; it < nch * (CH / 256); it += NW) {
+    const int c = it / (CH / 256);
     const int j1 = surfCnt[c0 + c];
     const float4* src = surf + base + (long long)c * CH;
-    // four loads in flight per lane: the sweep is latency-bound, not bandwidth-bound
-    {
-      const int j = (it % (CH / 128)) * 128 + lane;
-      if (j - lane >= j1) continue;
-      float4 q[4];
+    // eight loads in flight per lane (only x and y are needed here): the sweep is latency-bound
+    const int j = (it % (CH / 256)) * 256 + lane;
+    if (j - lane >= j1) continue;
+    float2 q[8];
 #pragma unroll
-      for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 8; k++) q[k] = (j + 32 * k < j1) ? *(const float2*)(src + j + 32 * k) : make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (j + 32 * k < j1) {
-          const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
-          atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
-        }
+    for (int k = 0; k < 8; k++) {
+      if (j + 32 * k < j1) {
+        const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
+        atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
       }
     }
   }
