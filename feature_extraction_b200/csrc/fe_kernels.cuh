@@ -34,6 +34,12 @@ constexpr int NTM = 64;
 constexpr int NTL = 1024;      // threads of the large K2 instantiation
 constexpr int ECAP_G = 65535;   // last resort: per-entry arrays in a global-memory slab (16-bit entry indices)
 constexpr int NGLOBAL = 32;     // blocks (and slabs) of the global-memory instantiations
+// cluster_extract tests all pairs of a ring while sum(n_r^2)/2 <= this * entries (0: never).  Ring
+// points are dense chains (a wall seen by one laser links every point to dozens of others, and
+// every link is a union): measured, the pair loop loses there at any threshold (K2 1.90 -> 1.97 ms
+// at 4 and 16, 3.95 ms at 256); ring centroids (K3) have few links and win at any size (0.26 -> 0.125 ms).
+constexpr int BRUTE_PAIRS_RINGS = 0;
+constexpr int BRUTE_PAIRS_MERGE = 256;
 constexpr int ECAP_L = 6144;    // the large instantiations (1 block / SM) for scans the fast ones defer
 
 // error bits reported through DevCounters::err
@@ -377,236 +383,288 @@ struct ClusterOut {
 // misc[96..127] is scratch.
 template <int NT>
 __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int minSz, int maxSz,
-                                int nRings, ClusterOut& out) {
+                                int nRings, int brutePairs, ClusterOut& out) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int* sc = S.misc + MAXCHUNK + 1;        // 128 ints of scratch
   float* bb = (float*)(sc + 40);          // 6 floats
-  // ---- bounding box of the entries (grid origin) ----
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int e = tid; e < E; e += NT) {
-    mn[0] = fminf(mn[0], S.x[e]); mx[0] = fmaxf(mx[0], S.x[e]);
-    mn[1] = fminf(mn[1], S.y[e]); mx[1] = fmaxf(mx[1], S.y[e]);
-    mn[2] = fminf(mn[2], S.z[e]); mx[2] = fmaxf(mx[2], S.z[e]);
-  }
-#pragma unroll
-  for (int k = 0; k < 3; k++)
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      mn[k] = fminf(mn[k], __shfl_xor_sync(FE_FULL, mn[k], d));
-      mx[k] = fmaxf(mx[k], __shfl_xor_sync(FE_FULL, mx[k], d));
-    }
-  float* red = (float*)(sc + 48);  // NT/32 * 6 floats <= 96 -> use S.wc area instead (free here)
-  red = (float*)S.wc;
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) { red[w * 6 + k] = mn[k]; red[w * 6 + 3 + k] = mx[k]; }
-  }
-  __syncthreads();
-  if (tid < 6) {
-    float v = red[tid];
-    for (int i = 1; i < NT / 32; i++) v = (tid < 3) ? fminf(v, red[i * 6 + tid]) : fmaxf(v, red[i * 6 + tid]);
-    bb[tid] = v;
-  }
-  __syncthreads();
-  // Grid cell = 0.55 * tolerance.  Two properties follow, both with several percent of slack
-  // against the float rounding of the cell computation and of the d2 predicate:
-  //   (i)  two points in the same cell are closer than sqrt(3)*0.55*tol = 0.953*tol: they are
-  //        linked by construction and need no distance test;
-  //   (ii) two linked points (d < tol) are at most 2 cells apart on every axis.
-  // Cell indices clamp to the key's bit budget (x,y: 10 bits, z: 8 bits); the monotone clamp keeps
-  // (ii), but merges far cells, so (i) is only trusted when nothing had to be clamped.
-  const float inv = 1.0f / (tol_f * 0.55f);
-  const float ox = bb[0], oy = bb[1], oz = bb[2];
-  const float fx = floorf((bb[3] - ox) * inv), fy = floorf((bb[4] - oy) * inv), fz = floorf((bb[5] - oz) * inv);
-  const bool trusted = (fx < 1023.0f) && (fy < 1023.0f) && (fz < 255.0f);
-  const int nx = (int)fminf(1023.0f, fmaxf(fx, 0.0f)) + 1;
-  const int ny = (int)fminf(1023.0f, fmaxf(fy, 0.0f)) + 1;
-  const int nz = (int)fminf(255.0f, fmaxf(fz, 0.0f)) + 1;
-  // key = ((ring*nz + cz)*ny + cy)*nx + cx  (< 2^32: 16 * 256 * 1024 * 1024)
-  const unsigned unx = (unsigned)nx, uny = (unsigned)ny, unz = (unsigned)nz;
-  const unsigned long long nkeys = (unsigned long long)nRings * unz * uny * unx;
-  const int keybits = (nkeys <= 1ull) ? 0 : 64 - __clzll((long long)(nkeys - 1ull));
-  // ---- keys ----
-  for (int e = tid; e < E; e += NT) {
-    int cx = (int)floorf((S.x[e] - ox) * inv), cy = (int)floorf((S.y[e] - oy) * inv), cz = (int)floorf((S.z[e] - oz) * inv);
-    cx = max(0, min(cx, nx - 1)); cy = max(0, min(cy, ny - 1)); cz = max(0, min(cz, nz - 1));
-    S.keyA[e] = (((unsigned)S.ring[e] * unz + (unsigned)cz) * uny + (unsigned)cy) * unx + (unsigned)cx;
-    S.valA[e] = (unsigned short)e;
-  }
-  // ---- radix sort of (key, entry) ----
+  // ---- small rings: all pairs inside every ring ----
+  // A ring of n entries costs n^2/2 distance tests (and a union per linked pair) here, against ~130 warp
+  // instructions per entry for the grid machinery below (keys, three radix passes, cells, row
+  // searches) that never tests points sharing a cell: the caller says up to which density this wins.
   unsigned *kS = S.keyA, *kT = S.keyB;
   unsigned short *vS = S.valA, *vT = S.valB;
-  for (int shift = 0; shift < keybits; shift += 8) {
-    unsigned* ki = kS; unsigned* ko = kT; unsigned short* vi = vS; unsigned short* vo = vT;
-    block_radix_pass<NT, unsigned short>(
-        E, [=](int i) { return (ki[i] >> shift) & 255u; },
-        [=](int i, int pos) { ko[pos] = ki[i]; vo[pos] = vi[i]; }, S.wc, S.base);
-    kS = ko; kT = ki; vS = vo; vT = vi;
-  }
-  __syncthreads();
-  // The last pass leaves in S.base[d] the end offset of top digit d: a 256-bucket index into the
-  // sorted keys that shortens every lower_bound below (keybits == 0: one bucket, no pass ran).
-  const int topShift = (keybits > 0) ? 8 * ((keybits - 1) >> 3) : 32;
-  const unsigned* bucketEnd = S.base;
-  // ---- units: the runs of equal key (cells); every entry on its own when cells are not trusted ----
-  unsigned short* unitStart = S.lst;
-  int nU = 0;
-  {
-    int run = 0;
-    for (int p0 = 0; p0 < E; p0 += NT) {
-      const int p = p0 + tid;
-      const int head = (p < E && (!trusted || p == 0 || kS[p] != kS[p - 1])) ? 1 : 0;
-      int tot;
-      const int pos = block_excl_scan<NT>(head, &tot, sc);
-      if (head) unitStart[run + pos] = (unsigned short)p;
-      if (p < E) S.aux[p] = (unsigned short)(run + pos + head - 1);  // unit index of every sorted position
-      run += tot;
+  bool brute = false;
+  if (brutePairs > 0) {
+    unsigned short* ord = S.valA;  // entries in ring order (stable: ascending entry inside a ring)
+    unsigned* ringEnd = S.base;    // block_radix_pass leaves the end offset of every digit (= ring)
+    if (nRings > 1) {
+      unsigned char* rng = S.ring;
+      block_radix_pass<NT, unsigned short>(
+          E, [=](int i) { return (unsigned)rng[i]; }, [=](int i, int pos) { ord[pos] = (unsigned short)i; }, S.wc, S.base);
+    } else {
+      for (int e = tid; e < E; e += NT) ord[e] = (unsigned short)e;
+      if (tid == 0) ringEnd[0] = (unsigned)E;
     }
-    nU = run;
-  }
-  __syncthreads();
-  // ---- union-find over sorted positions; a cell's members start out linked to its first ----
-  unsigned* parentS = kT;
-  constexpr int G = 8;
-  const int gl = lane & (G - 1);
-  const unsigned gmask = 0xFFu << (lane & 24);
-  unsigned short* unitOf = S.aux;
-  for (int p = tid; p < E; p += NT) parentS[p] = (unsigned)unitStart[unitOf[p]];
-  __syncthreads();
-  // One 8-lane group per unit.  The 13 rows (dz,dy) that precede the unit's own cell in key order
-  // and can hold linked points are located by 13 binary searches spread over the lanes; the
-  // candidates of a row are then visited 8 at a time.  A candidate already in the unit's component
-  // is skipped; otherwise it is tested against the unit's members until the first link.
-  int* unitCursor = sc + 60;
-  if (tid == 0) *unitCursor = 0;
-  __syncthreads();
-  for (;;) {
-    int u = 0;
-    if (gl == 0) u = atomicAdd(unitCursor, 1);  // units are handed out dynamically: their cost varies a lot
-    u = __shfl_sync(gmask, u, 0, G);
-    if (u >= nU) break;
-    const int a0 = unitStart[u];
-    const int a1 = (u + 1 < nU) ? (int)unitStart[u + 1] : E;
-    const unsigned key = kS[a0];
-    const int cx = (int)(key % unx);
-    const unsigned t1 = key / unx;
-    const int cy = (int)(t1 % uny);
-    const unsigned t2 = t1 / uny;
-    const int cz = (int)(t2 % unz);
-    const unsigned rg = t2 / unz;
-    int lo[2] = {0, 0}, end[2] = {0, 0};
-    unsigned khi[2] = {0u, 0u};
-    unsigned mine = 0;  // bit rnd: my row of that round has candidates
-#pragma unroll
-    for (int rnd = 0; rnd < 2; rnd++) {
-      const int r = gl + 8 * rnd;  // 0..9: dz=-2,-1 x dy=-2..2; 10,11: dz=0, dy=-2,-1; 12: own row
-      if (r < 13) {
-        const int dz = (r < 5) ? -2 : (r < 10) ? -1 : 0;
-        const int dy = (r < 10) ? (r % 5) - 2 : (r == 12) ? 0 : r - 12;
-        const int zz = cz + dz, yy = cy + dy;
-        if (zz >= 0 && yy >= 0 && yy < ny) {
-          const unsigned rowk = ((rg * unz + (unsigned)zz) * uny + (unsigned)yy) * unx;
-          const unsigned klo = rowk + (unsigned)max(cx - 2, 0);
-          khi[rnd] = rowk + (unsigned)min(cx + 2, nx - 1);
-          end[rnd] = (r == 12) ? a0 : E;
-          int l = 0, h = end[rnd];  // lower_bound(klo) in kS[0, end), inside klo's top-digit bucket
-          if (topShift < 32) {
-            const unsigned d = klo >> topShift;
-            l = min(d ? (int)bucketEnd[d - 1] : 0, h);
-            h = min((int)bucketEnd[d], h);
+    __syncthreads();
+    unsigned long long sumsq = 0;
+    for (int r = 0; r < nRings; r++) {
+      const unsigned long long nr = ringEnd[r] - (r ? ringEnd[r - 1] : 0u);
+      sumsq += nr * nr;
+    }
+    brute = sumsq <= (unsigned long long)brutePairs * 2ull * (unsigned long long)E;
+    if (brute) {
+      unsigned* par = S.keyB;
+      for (int e = tid; e < E; e += NT) par[e] = (unsigned)e;
+      __syncthreads();
+      for (int k = tid; k < E; k += NT) {
+        const unsigned ei = ord[k];
+        const int end = (int)ringEnd[S.ring[ei]];
+        const float xi = S.x[ei], yi = S.y[ei], zi = S.z[ei];
+        for (int m = k + 1; m < end; m++) {
+          const unsigned ej = ord[m];
+          if (l2_simple(xi, yi, zi, S.x[ej], S.y[ej], S.z[ej]) < r2f) {
+            const volatile unsigned* vp = par;
+            if (vp[ei] != vp[ej]) uf_union(par, ei, ej);
           }
-          while (l < h) {
-            const int mid = (l + h) >> 1;
-            if (kS[mid] < klo) l = mid + 1; else h = mid;
-          }
-          lo[rnd] = l;
-          if (l < end[rnd] && kS[l] <= khi[rnd]) mine |= 1u << rnd;
         }
       }
+      __syncthreads();
+      // flatten: the root of a component is its smallest entry (= its first point in the cloud)
+      for (int e = tid; e < E; e += NT) { const unsigned r = uf_find_readonly(par, (unsigned)e); S.aux[e] = (unsigned short)r; }
+      __syncthreads();
+      for (int e = tid; e < E; e += NT) { par[e] = S.aux[e]; S.keyA[e] = 0; }
+      __syncthreads();
     }
-    // rows that actually hold candidates: bit (8*rnd + lane)
-    unsigned rows = (__ballot_sync(gmask, mine & 1u) >> (lane & 24)) & 0xFFu;
-    rows |= ((__ballot_sync(gmask, mine & 2u) >> (lane & 24)) & 0xFFu) << 8;
-    while (rows) {
-      const int r = __ffs(rows) - 1;
-      rows &= rows - 1;
-      const int src = r & 7;
-      const int rlo = __shfl_sync(gmask, (r < 8) ? lo[0] : lo[1], src, G);
-      const int rend = __shfl_sync(gmask, (r < 8) ? end[0] : end[1], src, G);
-      const unsigned rkhi = __shfl_sync(gmask, (r < 8) ? khi[0] : khi[1], src, G);
-      // Candidate units (cells) of this row — at most five, one lane each.  All points of a unit are
-      // in one component, so one root comparison decides whether the unit matters.  Small unit pairs
-      // are tested by the lane that owns them; large ones (dense cells) are flagged and then tested
-      // by the whole group, the pair tests spread over the 8 lanes, stopping at the first link.
-      for (int uu0 = unitOf[rlo];; uu0 += G) {
-        const int uu = uu0 + gl;
-        bool in = false, heavy = false;
-        if (uu < nU) {
-          const int b0 = unitStart[uu];
-          in = (b0 < rend) && (kS[b0] <= rkhi);
-          if (in && uf_find(parentS, (unsigned)b0) != uf_find(parentS, (unsigned)a0)) {
-            const int b1 = (uu + 1 < nU) ? (int)unitStart[uu + 1] : E;
-            if ((a1 - a0) * (b1 - b0) <= 96) {
-              bool linked = false;
-              for (int a = a0; a < a1 && !linked; a++) {
-                const unsigned ea = vS[a];
-                const float ax = S.x[ea], ay = S.y[ea], az = S.z[ea];
-                for (int b = b0; b < b1; b++) {
-                  const unsigned eb = vS[b];
-                  if (l2_simple(ax, ay, az, S.x[eb], S.y[eb], S.z[eb]) < r2f) { linked = true; break; }
+  }
+  if (!brute) {
+    // ---- bounding box of the entries (grid origin) ----
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int e = tid; e < E; e += NT) {
+      mn[0] = fminf(mn[0], S.x[e]); mx[0] = fmaxf(mx[0], S.x[e]);
+      mn[1] = fminf(mn[1], S.y[e]); mx[1] = fmaxf(mx[1], S.y[e]);
+      mn[2] = fminf(mn[2], S.z[e]); mx[2] = fmaxf(mx[2], S.z[e]);
+    }
+  #pragma unroll
+    for (int k = 0; k < 3; k++)
+  #pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        mn[k] = fminf(mn[k], __shfl_xor_sync(FE_FULL, mn[k], d));
+        mx[k] = fmaxf(mx[k], __shfl_xor_sync(FE_FULL, mx[k], d));
+      }
+    float* red = (float*)(sc + 48);  // NT/32 * 6 floats <= 96 -> use S.wc area instead (free here)
+    red = (float*)S.wc;
+    __syncthreads();
+    if (lane == 0) {
+  #pragma unroll
+      for (int k = 0; k < 3; k++) { red[w * 6 + k] = mn[k]; red[w * 6 + 3 + k] = mx[k]; }
+    }
+    __syncthreads();
+    if (tid < 6) {
+      float v = red[tid];
+      for (int i = 1; i < NT / 32; i++) v = (tid < 3) ? fminf(v, red[i * 6 + tid]) : fmaxf(v, red[i * 6 + tid]);
+      bb[tid] = v;
+    }
+    __syncthreads();
+    // Grid cell = 0.55 * tolerance.  Two properties follow, both with several percent of slack
+    // against the float rounding of the cell computation and of the d2 predicate:
+    //   (i)  two points in the same cell are closer than sqrt(3)*0.55*tol = 0.953*tol: they are
+    //        linked by construction and need no distance test;
+    //   (ii) two linked points (d < tol) are at most 2 cells apart on every axis.
+    // Cell indices clamp to the key's bit budget (x,y: 10 bits, z: 8 bits); the monotone clamp keeps
+    // (ii), but merges far cells, so (i) is only trusted when nothing had to be clamped.
+    const float inv = 1.0f / (tol_f * 0.55f);
+    const float ox = bb[0], oy = bb[1], oz = bb[2];
+    const float fx = floorf((bb[3] - ox) * inv), fy = floorf((bb[4] - oy) * inv), fz = floorf((bb[5] - oz) * inv);
+    const bool trusted = (fx < 1023.0f) && (fy < 1023.0f) && (fz < 255.0f);
+    const int nx = (int)fminf(1023.0f, fmaxf(fx, 0.0f)) + 1;
+    const int ny = (int)fminf(1023.0f, fmaxf(fy, 0.0f)) + 1;
+    const int nz = (int)fminf(255.0f, fmaxf(fz, 0.0f)) + 1;
+    // key = ((ring*nz + cz)*ny + cy)*nx + cx  (< 2^32: 16 * 256 * 1024 * 1024)
+    const unsigned unx = (unsigned)nx, uny = (unsigned)ny, unz = (unsigned)nz;
+    const unsigned long long nkeys = (unsigned long long)nRings * unz * uny * unx;
+    const int keybits = (nkeys <= 1ull) ? 0 : 64 - __clzll((long long)(nkeys - 1ull));
+    // ---- keys ----
+    for (int e = tid; e < E; e += NT) {
+      int cx = (int)floorf((S.x[e] - ox) * inv), cy = (int)floorf((S.y[e] - oy) * inv), cz = (int)floorf((S.z[e] - oz) * inv);
+      cx = max(0, min(cx, nx - 1)); cy = max(0, min(cy, ny - 1)); cz = max(0, min(cz, nz - 1));
+      S.keyA[e] = (((unsigned)S.ring[e] * unz + (unsigned)cz) * uny + (unsigned)cy) * unx + (unsigned)cx;
+      S.valA[e] = (unsigned short)e;
+    }
+    // ---- radix sort of (key, entry) ----
+    kS = S.keyA; kT = S.keyB; vS = S.valA; vT = S.valB;
+    for (int shift = 0; shift < keybits; shift += 8) {
+      unsigned* ki = kS; unsigned* ko = kT; unsigned short* vi = vS; unsigned short* vo = vT;
+      block_radix_pass<NT, unsigned short>(
+          E, [=](int i) { return (ki[i] >> shift) & 255u; },
+          [=](int i, int pos) { ko[pos] = ki[i]; vo[pos] = vi[i]; }, S.wc, S.base);
+      kS = ko; kT = ki; vS = vo; vT = vi;
+    }
+    __syncthreads();
+    // The last pass leaves in S.base[d] the end offset of top digit d: a 256-bucket index into the
+    // sorted keys that shortens every lower_bound below (keybits == 0: one bucket, no pass ran).
+    const int topShift = (keybits > 0) ? 8 * ((keybits - 1) >> 3) : 32;
+    const unsigned* bucketEnd = S.base;
+    // ---- units: the runs of equal key (cells); every entry on its own when cells are not trusted ----
+    unsigned short* unitStart = S.lst;
+    int nU = 0;
+    {
+      int run = 0;
+      for (int p0 = 0; p0 < E; p0 += NT) {
+        const int p = p0 + tid;
+        const int head = (p < E && (!trusted || p == 0 || kS[p] != kS[p - 1])) ? 1 : 0;
+        int tot;
+        const int pos = block_excl_scan<NT>(head, &tot, sc);
+        if (head) unitStart[run + pos] = (unsigned short)p;
+        if (p < E) S.aux[p] = (unsigned short)(run + pos + head - 1);  // unit index of every sorted position
+        run += tot;
+      }
+      nU = run;
+    }
+    __syncthreads();
+    // ---- union-find over sorted positions; a cell's members start out linked to its first ----
+    unsigned* parentS = kT;
+    constexpr int G = 8;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = 0xFFu << (lane & 24);
+    unsigned short* unitOf = S.aux;
+    for (int p = tid; p < E; p += NT) parentS[p] = (unsigned)unitStart[unitOf[p]];
+    __syncthreads();
+    // One 8-lane group per unit.  The 13 rows (dz,dy) that precede the unit's own cell in key order
+    // and can hold linked points are located by 13 binary searches spread over the lanes; the
+    // candidates of a row are then visited 8 at a time.  A candidate already in the unit's component
+    // is skipped; otherwise it is tested against the unit's members until the first link.
+    int* unitCursor = sc + 60;
+    if (tid == 0) *unitCursor = 0;
+    __syncthreads();
+    for (;;) {
+      int u = 0;
+      if (gl == 0) u = atomicAdd(unitCursor, 1);  // units are handed out dynamically: their cost varies a lot
+      u = __shfl_sync(gmask, u, 0, G);
+      if (u >= nU) break;
+      const int a0 = unitStart[u];
+      const int a1 = (u + 1 < nU) ? (int)unitStart[u + 1] : E;
+      const unsigned key = kS[a0];
+      const int cx = (int)(key % unx);
+      const unsigned t1 = key / unx;
+      const int cy = (int)(t1 % uny);
+      const unsigned t2 = t1 / uny;
+      const int cz = (int)(t2 % unz);
+      const unsigned rg = t2 / unz;
+      int lo[2] = {0, 0}, end[2] = {0, 0};
+      unsigned khi[2] = {0u, 0u};
+      unsigned mine = 0;  // bit rnd: my row of that round has candidates
+  #pragma unroll
+      for (int rnd = 0; rnd < 2; rnd++) {
+        const int r = gl + 8 * rnd;  // 0..9: dz=-2,-1 x dy=-2..2; 10,11: dz=0, dy=-2,-1; 12: own row
+        if (r < 13) {
+          const int dz = (r < 5) ? -2 : (r < 10) ? -1 : 0;
+          const int dy = (r < 10) ? (r % 5) - 2 : (r == 12) ? 0 : r - 12;
+          const int zz = cz + dz, yy = cy + dy;
+          if (zz >= 0 && yy >= 0 && yy < ny) {
+            const unsigned rowk = ((rg * unz + (unsigned)zz) * uny + (unsigned)yy) * unx;
+            const unsigned klo = rowk + (unsigned)max(cx - 2, 0);
+            khi[rnd] = rowk + (unsigned)min(cx + 2, nx - 1);
+            end[rnd] = (r == 12) ? a0 : E;
+            int l = 0, h = end[rnd];  // lower_bound(klo) in kS[0, end), inside klo's top-digit bucket
+            if (topShift < 32) {
+              const unsigned d = klo >> topShift;
+              l = min(d ? (int)bucketEnd[d - 1] : 0, h);
+              h = min((int)bucketEnd[d], h);
+            }
+            while (l < h) {
+              const int mid = (l + h) >> 1;
+              if (kS[mid] < klo) l = mid + 1; else h = mid;
+            }
+            lo[rnd] = l;
+            if (l < end[rnd] && kS[l] <= khi[rnd]) mine |= 1u << rnd;
+          }
+        }
+      }
+      // rows that actually hold candidates: bit (8*rnd + lane)
+      unsigned rows = (__ballot_sync(gmask, mine & 1u) >> (lane & 24)) & 0xFFu;
+      rows |= ((__ballot_sync(gmask, mine & 2u) >> (lane & 24)) & 0xFFu) << 8;
+      while (rows) {
+        const int r = __ffs(rows) - 1;
+        rows &= rows - 1;
+        const int src = r & 7;
+        const int rlo = __shfl_sync(gmask, (r < 8) ? lo[0] : lo[1], src, G);
+        const int rend = __shfl_sync(gmask, (r < 8) ? end[0] : end[1], src, G);
+        const unsigned rkhi = __shfl_sync(gmask, (r < 8) ? khi[0] : khi[1], src, G);
+        // Candidate units (cells) of this row — at most five, one lane each.  All points of a unit are
+        // in one component, so one root comparison decides whether the unit matters.  Small unit pairs
+        // are tested by the lane that owns them; large ones (dense cells) are flagged and then tested
+        // by the whole group, the pair tests spread over the 8 lanes, stopping at the first link.
+        for (int uu0 = unitOf[rlo];; uu0 += G) {
+          const int uu = uu0 + gl;
+          bool in = false, heavy = false;
+          if (uu < nU) {
+            const int b0 = unitStart[uu];
+            in = (b0 < rend) && (kS[b0] <= rkhi);
+            if (in && uf_find(parentS, (unsigned)b0) != uf_find(parentS, (unsigned)a0)) {
+              const int b1 = (uu + 1 < nU) ? (int)unitStart[uu + 1] : E;
+              if ((a1 - a0) * (b1 - b0) <= 96) {
+                bool linked = false;
+                for (int a = a0; a < a1 && !linked; a++) {
+                  const unsigned ea = vS[a];
+                  const float ax = S.x[ea], ay = S.y[ea], az = S.z[ea];
+                  for (int b = b0; b < b1; b++) {
+                    const unsigned eb = vS[b];
+                    if (l2_simple(ax, ay, az, S.x[eb], S.y[eb], S.z[eb]) < r2f) { linked = true; break; }
+                  }
                 }
+                if (linked) uf_union(parentS, (unsigned)a0, (unsigned)b0);
+              } else {
+                heavy = true;
               }
-              if (linked) uf_union(parentS, (unsigned)a0, (unsigned)b0);
-            } else {
-              heavy = true;
             }
           }
-        }
-        unsigned hv = (__ballot_sync(gmask, heavy) >> (lane & 24)) & 0xFFu;
-        while (hv) {
-          const int ub = uu0 + __ffs(hv) - 1;
-          hv &= hv - 1;
-          const int b0 = unitStart[ub];
-          const int b1 = (ub + 1 < nU) ? (int)unitStart[ub + 1] : E;
-          int differs = 0;  // re-checked (unions happened meanwhile); by lane 0 so that it is uniform
-          if (gl == 0) differs = (uf_find(parentS, (unsigned)b0) != uf_find(parentS, (unsigned)a0)) ? 1 : 0;
-          differs = __shfl_sync(gmask, differs, 0, G);
-          if (!differs) continue;
-          bool linked = false;
-          for (int a = a0; a < a1; a++) {
-            const unsigned ea = vS[a];
-            const float ax = S.x[ea], ay = S.y[ea], az = S.z[ea];
-            for (int b = b0 + gl; b < b1; b += G) {
-              const unsigned eb = vS[b];
-              if (l2_simple(ax, ay, az, S.x[eb], S.y[eb], S.z[eb]) < r2f) { linked = true; break; }
+          unsigned hv = (__ballot_sync(gmask, heavy) >> (lane & 24)) & 0xFFu;
+          while (hv) {
+            const int ub = uu0 + __ffs(hv) - 1;
+            hv &= hv - 1;
+            const int b0 = unitStart[ub];
+            const int b1 = (ub + 1 < nU) ? (int)unitStart[ub + 1] : E;
+            int differs = 0;  // re-checked (unions happened meanwhile); by lane 0 so that it is uniform
+            if (gl == 0) differs = (uf_find(parentS, (unsigned)b0) != uf_find(parentS, (unsigned)a0)) ? 1 : 0;
+            differs = __shfl_sync(gmask, differs, 0, G);
+            if (!differs) continue;
+            bool linked = false;
+            for (int a = a0; a < a1; a++) {
+              const unsigned ea = vS[a];
+              const float ax = S.x[ea], ay = S.y[ea], az = S.z[ea];
+              for (int b = b0 + gl; b < b1; b += G) {
+                const unsigned eb = vS[b];
+                if (l2_simple(ax, ay, az, S.x[eb], S.y[eb], S.z[eb]) < r2f) { linked = true; break; }
+              }
+              if (__ballot_sync(gmask, linked) != 0u) { linked = true; break; }
             }
-            if (__ballot_sync(gmask, linked) != 0u) { linked = true; break; }
+            if (linked && gl == 0) uf_union(parentS, (unsigned)a0, (unsigned)b0);
           }
-          if (linked && gl == 0) uf_union(parentS, (unsigned)a0, (unsigned)b0);
+          if (!__shfl_sync(gmask, (int)in, G - 1, G)) break;  // units are in key order: nothing further in range
         }
-        if (!__shfl_sync(gmask, (int)in, G - 1, G)) break;  // units are in key order: nothing further in range
       }
     }
+    __syncthreads();
+    // ---- flatten; label every component with its smallest entry (= its first point in the cloud) ----
+    for (int p = tid; p < E; p += NT) parentS[p] = uf_find_readonly(parentS, (unsigned)p);
+    __syncthreads();
+    unsigned* minE = kS;
+    for (int p = tid; p < E; p += NT) minE[p] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int p = tid; p < E; p += NT) atomicMin(&minE[parentS[p]], (unsigned)vS[p]);
+    __syncthreads();
+    for (int p = tid; p < E; p += NT) {
+      vT[p] = (unsigned short)minE[parentS[p]];
+      S.aux[vS[p]] = (unsigned short)p;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // ---- flatten; label every component with its smallest entry (= its first point in the cloud) ----
-  for (int p = tid; p < E; p += NT) parentS[p] = uf_find_readonly(parentS, (unsigned)p);
-  __syncthreads();
-  unsigned* minE = kS;
-  for (int p = tid; p < E; p += NT) minE[p] = 0xFFFFFFFFu;
-  __syncthreads();
-  for (int p = tid; p < E; p += NT) atomicMin(&minE[parentS[p]], (unsigned)vS[p]);
-  __syncthreads();
-  for (int p = tid; p < E; p += NT) {
-    vT[p] = (unsigned short)minE[parentS[p]];
-    S.aux[vS[p]] = (unsigned short)p;
-  }
-  __syncthreads();
   unsigned* parent = kT;  // from here on indexed by entry: parent[e] = first entry of e's component
   unsigned* cnt = kS;
-  for (int e = tid; e < E; e += NT) { parent[e] = vT[S.aux[e]]; cnt[e] = 0; }
-  __syncthreads();
+  if (!brute) {
+    for (int e = tid; e < E; e += NT) { parent[e] = vT[S.aux[e]]; cnt[e] = 0; }
+    __syncthreads();
+  }
   for (int e = tid; e < E; e += NT) atomicAdd(&cnt[parent[e]], 1u);
   __syncthreads();
   // ---- size-gated roots in discovery order (ascending first member) ----
@@ -815,7 +873,7 @@ __device__ void cluster_rings_scan(
       __syncthreads();
       const int E = run;
       ClusterOut C;
-      cluster_extract<NT>(S, E, P.tol_f, P.r2f_cluster, P.min_count, P.max_count, r1 - r0, C);
+      cluster_extract<NT>(S, E, P.tol_f, P.r2f_cluster, P.min_count, P.max_count, r1 - r0, BRUTE_PAIRS_RINGS, C);
       // ---- getCylinderSegments gate + centroid per cluster (src:282-325), one thread each ----
       int* sh = sc + 100;  // [0] = pool base, [1] = kc base
       int runG = 0, runM = 0;
@@ -971,7 +1029,7 @@ __device__ void merge_keypoints_scan(
   }
   __syncthreads();
   ClusterOut C;
-  cluster_extract<NT>(S, Kf, P.merge_tol_f, P.r2f_merge, P.min_channels, 16, 1, C);
+  cluster_extract<NT>(S, Kf, P.merge_tol_f, P.r2f_merge, P.min_channels, 16, 1, BRUTE_PAIRS_MERGE, C);
   if (C.nC == 0) return;
   int* sh = sc + 100;
   if (tid == 0) {
@@ -1043,7 +1101,7 @@ __global__ void __launch_bounds__(NT2, 1) k_extract_clusters_stage(
   }
   __syncthreads();
   ClusterOut C;
-  cluster_extract<NT2>(S, n, tol_f, r2f, minSz, maxSz, 1, C);
+  cluster_extract<NT2>(S, n, tol_f, r2f, minSz, maxSz, 1, BRUTE_PAIRS_RINGS, C);
   if (tid == 0) { nOut[0] = C.nC; offsets[0] = 0; }
   if (C.nC > capClusters) return;
   for (int i = tid; i < C.nC; i += NT2) {
