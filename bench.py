@@ -187,6 +187,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL's own log lines (e.g. its version banner) go to stderr: stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cfg = args.config
