@@ -306,7 +306,8 @@ std::string err_bits(int e) {
 
 // Host-side staging of the small per-scan arrays of a sub-batch.  offs are absolute offsets of
 // the caller's array; the device sees offsets relative to the first point of the sub-batch.
-int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int nscans, int64_t* nptsOut, int* nchOut) {
+int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int nscans, int64_t* nptsOut, int* nchOut,
+                bool deferRot = false) {
   const int64_t o0 = offs[0];
   int nch = 0;
   for (int i = 0; i < nscans; i++) {
@@ -315,6 +316,7 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
     s.h_scan_off[i] = (long long)(offs[i] - o0);
     s.h_chunk_off[i] = nch;
     nch += (int)((n + CH - 1) / CH);
+    if (deferRot) continue;  // enqueue_pipeline computes the matrices range by range (lateRp)
     if (rp) leveling_matrix(rp[2 * i], rp[2 * i + 1], s.h_rot + 9 * i);
     else { float* m = s.h_rot + 9 * i; for (int k = 0; k < 9; k++) m[k] = (k % 4 == 0) ? 1.0f : 0.0f; }
   }
@@ -327,7 +329,7 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
   if (nch > s.capChunks) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds the chunk capacity");
   CK(cudaMemcpyAsync(s.d_scan_off, s.h_scan_off, (nscans + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_chunk_off, s.h_chunk_off, (nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-  CK(cudaMemcpyAsync(s.d_rot, s.h_rot, (size_t)nscans * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+  if (!deferRot) CK(cudaMemcpyAsync(s.d_rot, s.h_rot, (size_t)nscans * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
   return FE_OK;
 }
 
@@ -492,19 +494,40 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
 // Enqueue the kernels of one sub-batch whose points are at d_pts.  k1flags selects what K1 does;
 // `fromStage`: 0 = K1 first; 1 = crop/cropMeta/cropCnt already filled by the caller.
 int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int64_t npts, int nch,
-                     int k1flags, bool doDesc, bool singleRing, bool wantKc, RawLayout lay = RawLayout{nullptr, 0, 0, 0, 0}) {
+                     int k1flags, bool doDesc, bool singleRing, bool wantKc, RawLayout lay = RawLayout{nullptr, 0, 0, 0, 0},
+                     const double* lateRp = nullptr) {
   DevParams& P = ctx->dp;
   s.nev = 0;
   mark(ctx, s, "begin");
   CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), s.stream));
   if (nch > 0 && k1flags >= 0) {
-    if (lay.raw)
-      k_level_crop_ring<true, true><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
-                                                         s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
-    else
-      k_level_crop_ring<false, true><<<nch, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
-                                                          s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay);
-    ctx->launches++;
+    // With `lateRp` the levelling matrices (two sincos and a quaternion product per scan on the host,
+    // ~0.4 ms for 10 k scans) are not staged yet: they are computed range by range — an eighth, an
+    // eighth, a quarter, a half of the scans — and K1 is launched per range, so that all but the first
+    // eighth of that host work runs while the GPU is already busy.  (16 equal ranges were measured:
+    // slower, the per-range copy and launch calls starve the GPU.)
+    const int cuts[5] = {0, nscans / 8, nscans / 4, nscans / 2, nscans};
+    const int nparts = lateRp ? 4 : 1;
+    for (int part = 0; part < nparts; part++) {
+      const int a = lateRp ? cuts[part] : 0, b = lateRp ? cuts[part + 1] : nscans;
+      if (b <= a) continue;
+      if (lateRp) {
+        for (int i = a; i < b; i++) leveling_matrix(lateRp[2 * i], lateRp[2 * i + 1], s.h_rot + 9 * i);
+        CK(cudaMemcpyAsync(s.d_rot + 9 * (size_t)a, s.h_rot + 9 * (size_t)a, (size_t)(b - a) * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        // stage times: whatever the GPU waited for the host goes to its own line, not to K1
+        if (part == 0) { s.nev = 0; mark(ctx, s, "begin"); } else mark(ctx, s, "host: levelling matrices");
+      }
+      const int ca = s.h_chunk_off[a], cb = s.h_chunk_off[b];
+      if (cb <= ca) continue;
+      if (lay.raw)
+        k_level_crop_ring<true, true><<<cb - ca, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+                                                               s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay, ca);
+      else
+        k_level_crop_ring<false, true><<<cb - ca, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+                                                                s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay, ca);
+      ctx->launches++;
+      if (lateRp && part + 1 < nparts) mark(ctx, s, "K1 level+crop+ring");
+    }
   }
   mark(ctx, s, "K1 level+crop+ring");
   launch_clustering(ctx, s, nscans, singleRing, wantKc, true, true);
@@ -896,10 +919,12 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int
   ctx->kpOffsets.assign((size_t)n_scans + 1, 0);
   int64_t npts = 0; int nch = 0;
   if (n_scans > 0) {
-    st = stage_scans(ctx, s, scan_offsets, roll_pitch, n_scans, &npts, &nch);
+    const bool late = n_scans >= 2048;
+    st = stage_scans(ctx, s, scan_offsets, roll_pitch, n_scans, &npts, &nch, late);
     if (st) return st;
     st = enqueue_pipeline(ctx, s, (const float4*)d_points + scan_offsets[0], n_scans, npts, nch,
-                          F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, false);
+                          F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, false,
+                          RawLayout{nullptr, 0, 0, 0, 0}, late ? roll_pitch : nullptr);
     if (st) return st;
     CK(cudaEventSynchronize(s.evDone));
     if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
@@ -990,7 +1015,7 @@ static int stage_k1(fe_ctx* ctx, fe_point_t* cloud, int64_t n, double roll, doub
   if (st) return st;
   CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   k_level_crop_ring<false, false><<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
-                                               s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full, RawLayout{nullptr, 0, 0, 0, 0});
+                                               s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full, RawLayout{nullptr, 0, 0, 0, 0}, 0);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(cloud, s.d_full, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
@@ -1025,7 +1050,7 @@ static int stage_upload_k1(fe_ctx* ctx, Slot& s, const fe_point_t* in, int64_t n
   if (n > 0) CK(cudaMemcpyAsync(s.d_pts, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   if (*nchOut > 0) {
     k_level_crop_ring<false, false><<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
-                                                     s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, RawLayout{nullptr, 0, 0, 0, 0});
+                                                     s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, RawLayout{nullptr, 0, 0, 0, 0}, 0);
     ctx->launches++;
   }
   CK(cudaGetLastError());

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
     const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
     int flags_rt, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
     unsigned* __restrict__ cropMeta, int* __restrict__ cropCnt, float4* __restrict__ full_out,
-    RawLayout L) {
+    RawLayout L, int chunk_base) {
   // FUSED: the cloudCallback path, every stage on (surface stream optional); otherwise run-time flags
   const int flags = FUSED ? (F_ELEV | F_ROT | F_CROP | F_RING | (flags_rt & F_SURF)) : flags_rt;
   __shared__ int s_scan;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
   // transformed points waiting for their output offsets.
   __shared__ __align__(128) float4 s_o[CH];
   __shared__ __align__(8) unsigned long long s_bar;
-  const int chunk = blockIdx.x;
+  const int chunk = chunk_base + blockIdx.x;  // a batch may be launched in several chunk ranges
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) {
     int lo = 0, hi = n_scans - 1;  // largest s with chunk_off[s] <= chunk
