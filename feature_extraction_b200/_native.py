@@ -21,7 +21,7 @@ EXPORTS = [
     "fe_destroy", "fe_last_error", "fe_device_count", "fe_host_alloc", "fe_host_free",
     "fe_process_batch", "fe_process_batch_layout", "fe_imu_to_roll_pitch", "fe_process_batch_device", "fe_download",
     "fe_multi_create", "fe_multi_process_batch", "fe_multi_destroy", "fe_multi_last_error", "fe_enable_cloud_outputs", "fe_get_cloud_outputs", "fe_enable_record_output", "fe_multi_enable_record_output",
-    "fe_get_stage_times", "fe_timer_begin", "fe_timer_end", "fe_get_batch_stats", "fe_get_elevation_angles", "fe_rotate_cloud", "fe_rotation_matrix",
+    "fe_get_stage_times", "fe_enable_stage_timing", "fe_timer_begin", "fe_timer_end", "fe_get_batch_stats", "fe_get_elevation_angles", "fe_rotate_cloud", "fe_rotation_matrix",
     "fe_filter_cloud", "fe_extract_clusters", "fe_get_cylinder_segments", "fe_estimate_keypoints",
     "fe_estimate_descriptors", "fe_pack_point_descriptors",
 ]
@@ -109,6 +109,7 @@ def lib():
         L.fe_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.fe_enable_cloud_outputs.argtypes = [C.c_void_p, C.c_int32]
         L.fe_enable_record_output.argtypes = [C.c_void_p, C.c_int32]
+        L.fe_enable_stage_timing.argtypes = [C.c_void_p, C.c_int32]
         L.fe_multi_enable_record_output.argtypes = [C.c_void_p, C.c_int32]
         L.fe_get_cloud_outputs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_void_p),
                                            C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_void_p)]

@@ -54,6 +54,10 @@ struct Slot {
   int* h_kpOff = nullptr;
   int* h_perScan = nullptr;
   cudaEvent_t evDone = nullptr, evT0 = nullptr, evT1 = nullptr;
+  // K4a depends on K1 only: it runs on a side stream next to K2/K3 (fork after K1, join before K4b)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  bool sideK4a = false;  // the pipeline in flight uses the side stream
   int lastNch = 0;
   // bookkeeping of the sub-batch in flight
   int nscans = 0;
@@ -78,6 +82,7 @@ struct fe_ctx {
   float2* d_axes = nullptr;
   int axesCap = 0;
   bool cloudOutputs = false;
+  bool stageTiming = false;   // serialise the stages and time each with CUDA events (fe_enable_stage_timing)
   bool recordOutput = false;  // descriptors leave as FE_RECORD_FLOATS-float PointDescriptor records
   // results (host, pinned, grown on demand)
   std::vector<int64_t> kpOffsets;
@@ -233,6 +238,8 @@ void free_slot(Slot& s) {
   if (s.evDone) cudaEventDestroy(s.evDone);
   if (s.evT0) cudaEventDestroy(s.evT0);
   if (s.evT1) cudaEventDestroy(s.evT1);
+  for (cudaEvent_t e : {s.evFork, s.evJoin}) if (e) cudaEventDestroy(e);
+  if (s.stream2) cudaStreamDestroy(s.stream2);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
 }
@@ -250,6 +257,9 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   s.capKf = (int)L.max_ring_clusters_per_call;
   s.capKc = 0;
   CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s.evFork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s.evJoin, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming));
   CK(cudaEventCreate(&s.evT0));
   CK(cudaEventCreate(&s.evT1));
@@ -284,12 +294,11 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
 }
 
 void mark(fe_ctx* ctx, Slot& s, const char* name) {
-  if (s.nev < (int)s.ev.size()) {
+  if (ctx->stageTiming && s.nev < (int)s.ev.size()) {
     cudaEventRecord(s.ev[s.nev], s.stream);
     s.evName[s.nev] = name;
     s.nev++;
   }
-  (void)ctx;
 }
 
 std::string err_bits(int e) {
@@ -435,18 +444,18 @@ void launch_desc_mark(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
 
 // K4a: counting sort by cell in shared memory for scans that fit (<= 65,535 surface points, grid <=
 // SURF_MAX_CELLS cells), radix sort through global memory for the deferred rest.
-void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
+void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, cudaStream_t q) {
   const int ncells = P.sg_nx * P.sg_ny;
   if (ncells <= SURF_MAX_CELLS) {
-    k_surface_grid_cells<NT_SURF><<<nscans, NT_SURF, surf_cells_smem_bytes(ncells), s.stream>>>(
+    k_surface_grid_cells<NT_SURF><<<nscans, NT_SURF, surf_cells_smem_bytes(ncells), q>>>(
         s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf,
         s.d_cellTab, s.d_tabOk);
-    k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
+    k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
                                                                    s.d_keyB, s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey,
                                                                    s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf,
                                                                    s.d_tabOk);
   } else {
-    k_surface_grid<<<nscans, NT2, 0, s.stream>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA,
+    k_surface_grid<<<nscans, NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA,
                                                  s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, nullptr, nullptr,
                                                  s.d_tabOk);
   }
@@ -530,6 +539,22 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     }
   }
   mark(ctx, s, "K1 level+crop+ring");
+  s.sideK4a = false;
+  if (doDesc) {
+    int st = ensure_rowstart(ctx, s, nscans);
+    if (st) return st;
+  }
+  if (doDesc && !ctx->stageTiming) {
+    // K4a (HBM-bound) needs K1's surface stream only: it runs on the side stream while K2/K3 (latency /
+    // issue bound, little HBM traffic) occupy the main one, and is joined before K4b.  With stage timing
+    // on, the stages run one after the other instead, so that every event pair brackets one stage alone.
+    CK(cudaEventRecord(s.evFork, s.stream));
+    CK(cudaStreamWaitEvent(s.stream2, s.evFork, 0));
+    CK(cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(npts, 1) * sizeof(int), s.stream2));
+    launch_surface_grid(ctx, s, nscans, P, s.stream2);
+    CK(cudaEventRecord(s.evJoin, s.stream2));
+    s.sideK4a = true;
+  }
   launch_clustering(ctx, s, nscans, singleRing, wantKc, true, true);
   mark(ctx, s, "K3 merge keypoints");
   k_kp_offsets<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr);
@@ -539,11 +564,13 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
   ctx->launches++;
   mark(ctx, s, "keypoint CSR");
   if (doDesc) {
-    int st = ensure_rowstart(ctx, s, nscans);
-    if (st) return st;
-    CK(cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(npts, 1) * sizeof(int), s.stream));
-    launch_surface_grid(ctx, s, nscans, P);
-    mark(ctx, s, "K4a surface grid");
+    if (s.sideK4a) {
+      CK(cudaStreamWaitEvent(s.stream, s.evJoin, 0));
+    } else {
+      CK(cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(npts, 1) * sizeof(int), s.stream));
+      launch_surface_grid(ctx, s, nscans, P, s.stream);
+      mark(ctx, s, "K4a surface grid");
+    }
     const int gridKp = 148 * 8;
     launch_desc_mark(ctx, s, nscans, P, gridKp);
     mark(ctx, s, "K4b mark neighbours");
@@ -754,6 +781,13 @@ void fe_destroy(fe_ctx_t* ctx) {
 int fe_enable_cloud_outputs(fe_ctx_t* ctx, int32_t enable) {
   if (!ctx) return FE_ERR_INVALID;
   ctx->cloudOutputs = enable != 0;
+  return FE_OK;
+}
+
+int fe_enable_stage_timing(fe_ctx_t* ctx, int32_t enable) {
+  if (!ctx) return FE_ERR_INVALID;
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+  ctx->stageTiming = enable != 0;
   return FE_OK;
 }
 
@@ -1219,7 +1253,7 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
       cudaMemcpyAsync(s.d_kpOut, keypoints, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, q) != cudaSuccess ||
       cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(int), q) != cudaSuccess)
     return restore(fail(ctx, FE_ERR_CUDA, "staging of the descriptor inputs failed"));
-  launch_surface_grid(ctx, s, 1, P);
+  launch_surface_grid(ctx, s, 1, P, s.stream);
   launch_desc_mark(ctx, s, 1, P, 148 * 4);
   if (n > 0) {
     k_density<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 64), 256, 0, q>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P,

@@ -300,6 +300,10 @@ class FeatureExtractionNode:
                 "deferred_ring_scans", "deferred_merge_scans", "deferred_surface_scans", "descriptors_unordered")
         return dict(zip(keys, (int(v) for v in out)))
 
+    def enableStageTiming(self, enable=True):
+        """fe_enable_stage_timing: serialise the stages and time each one (see stageTimes)."""
+        self._check(N.lib().fe_enable_stage_timing(self._ctx, 1 if enable else 0))
+
     def stageTimes(self):
         names = (C.c_char_p * 32)()
         ms = (C.c_float * 32)()

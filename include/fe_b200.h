@@ -176,7 +176,11 @@ int fe_timer_end(fe_ctx_t* ctx, float* elapsed_ms);
  * global-memory K4a, keypoints whose descriptor was summed out of PCL's order (> 8192 contributions). */
 int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[10]);
 
-/* Per-kernel CUDA-event times (ms) of the last device call; names are static strings. */
+/* Per-kernel CUDA-event times (ms) of the last device call; names are static strings.  Only collected
+ * after fe_enable_stage_timing(ctx, 1), which also makes the stages run strictly one after the other
+ * (by default the surface-grid kernel runs on a side stream next to the clustering kernels, so an
+ * event pair around one of them would time both). */
+int fe_enable_stage_timing(fe_ctx_t* ctx, int32_t enable);
 int fe_get_stage_times(fe_ctx_t* ctx, int32_t cap, const char** names, float* ms, int32_t* n);
 
 /* ---- one entry point per reference function (host buffers, synchronous) ------------------ */
