@@ -158,7 +158,7 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
         "mpoints_per_s": v * float(offs[-1]) / n / 1e6,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def stage_bytes(st, desc_len=1980):
@@ -176,8 +176,31 @@ def stage_bytes(st, desc_len=1980):
     }
 
 
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: whatever libraries print there at C level (NCCL's version
+    banner, ...) is sent to stderr for the duration of the run; the result goes to the original fd."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(out):
+    line = (json.dumps(out) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, line)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,8 +214,6 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL's own log lines (e.g. its version banner) go to stderr: stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cfg = args.config
@@ -377,7 +398,7 @@ def main():
         same = bool(np.array_equal(ko[: n + 1], ko_o) and np.array_equal(kp[: ko[n]].view(np.uint32), kp_o.view(np.uint32)))
         out["parity_vs_oracle_on_sample"] = same
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     host_node.close()
     pin.free()
     if world > 1:
