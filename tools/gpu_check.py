@@ -64,6 +64,7 @@ for cfg in (1, 2, 3, 4):
                 print("    per-kp max rel:", np.nanmax(rel, axis=1)[:12], "margin", r['edge_margin'][:12])
     # fused batch
     nd.enableCloudOutputs(True)
+    nd.enableStageTiming(True)
     ko, kp, d = nd.processBatch(pts, offs, rp)
     ko_o, kp_o, d_o, m_o = ob.process_batch(P, pts, offs, rp, mode=0, n_threads=8, want_margin=True)
     cmp("BATCH keypoint_offsets", ko, ko_o); cmp("BATCH keypoints", kp, kp_o)
@@ -77,6 +78,7 @@ for cfg in (1, 2, 3, 4):
 # throughput smoke: config 2, 2000 scans
 pts, offs, rp = synth.generate(2, 2000)
 nd = fn.FeatureExtractionNode(to_fe(ob.node_default()), max_points=40 << 20, max_scans=2048, max_keypoints=1 << 17)
+nd.enableStageTiming(True)
 for it in range(3):
     t = time.time(); ko, kp, d = nd.processBatch(pts, offs, rp, copy=False); dt = time.time() - t
     print("config2 x2000: %.1f ms -> %.0f scans/s, K=%d" % (dt * 1e3, 2000 / dt, len(kp)), nd.stageTimes())
