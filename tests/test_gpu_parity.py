@@ -241,3 +241,29 @@ def test_record_output_equals_concatenate_fields_on_the_host(ob, synth, nodes):
     ko6, kp6, rec6 = r.processBatch(pts, offs, rp)
     r.close()
     assert rec6 is None and bits_equal(kp6, kp)
+
+
+def test_stage_timing_mode_serialises_without_changing_results(ob, synth, nodes):
+    """fe_enable_stage_timing: the surface-grid kernel leaves its side stream, every stage gets a
+    CUDA-event pair; results stay bit-identical and fe_get_stage_times reports the stages."""
+    import torch
+    nd = nodes(2)
+    pts, offs, rp = synth.generate(2, 48, scan_index_base=4100)
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    assert nd.stageTimes() == []                      # not collected by default
+    nd.enableStageTiming(True)
+    try:
+        ko2, kp2, d2 = nd.processBatch(pts, offs, rp)
+        names = [n for n, ms in nd.stageTimes()]
+        dev = torch.from_numpy(pts).cuda()
+        torch.cuda.synchronize()
+        ko3, K, p_kp, p_d = nd.processBatchDevice(dev.data_ptr(), offs, rp)
+        names_dev = [n for n, ms in nd.stageTimes()]
+        d3 = nd.download(p_d, (K, 1980))
+    finally:
+        nd.enableStageTiming(False)
+    assert np.array_equal(ko, ko2) and bits_equal(kp, kp2) and bits_equal(d, d2)
+    assert np.array_equal(ko, ko3) and bits_equal(d, d3)
+    for want in ("K1 level+crop+ring", "K2 ring clusters", "K3 merge keypoints", "K4a surface grid", "K4b mark neighbours",
+                 "K4c density", "K4d shape context"):
+        assert want in names and want in names_dev
