@@ -80,15 +80,20 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    def __init__(self, gpu_indices):
+        """One poller for ALL GPUs of the job (rank 0 starts it; ranks > 0 pass None): a poller per rank
+        multiplies the driver queries without adding information."""
+        self.gpus = gpu_indices
         self.rows = []
         self.proc = None
 
     def start(self):
+        if self.gpus is None:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(g) for g in self.gpus), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100" if len(self.gpus) == 1 else "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -99,6 +104,8 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.gpus is None:
+            return None
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -122,7 +129,7 @@ class ClockSampler:
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus": list(self.gpus)}
 
 
 def host_threads():
@@ -249,7 +256,9 @@ def main():
     # ---- value: device-resident hot path ----
     # clocks / throttle reasons are sampled from before the warm-up to the end of the e2e phase (the
     # device-resident timed region alone is shorter than one nvidia-smi sampling period)
-    sampler = ClockSampler(local_rank)
+    phys = [g.strip() for g in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if g.strip()]
+    job_gpus = [phys[i] if i < len(phys) else i for i in range(world)]  # nvidia-smi wants physical indices / UUIDs
+    sampler = ClockSampler(job_gpus if rank == 0 else None)
     sampler.start()
     for _ in range(args.warmup):
         dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
