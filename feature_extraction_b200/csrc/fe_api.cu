@@ -408,9 +408,11 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
 #define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, \
                      s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, FE_DESC_LIST, s.d_desc, descStride, descOff, s.d_ctr
   // the blocks stride over the keypoints with equal shares: grids of exactly one resident wave
-  static int perSm = 0;
-  if (!perSm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_desc_hist<256, DCAP, 0, false>, 256,
-                                                              desc_smem_bytes(DCAP, 256)) != cudaSuccess) perSm = 4;
+  static const int perSm = []() {  // initialised once, also when fe_multi's threads get here together
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist<256, DCAP, 0, false>, 256, desc_smem_bytes(DCAP, 256)) != cudaSuccess) v = 4;
+    return v;
+  }();
 #define FE_DESC_LIST nullptr, nullptr
   k_desc_hist<256, DCAP, 0, false><<<std::min(gridKp, 148 * std::max(perSm, 1)), 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
@@ -432,8 +434,11 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
 void launch_desc_mark(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp) {
   const long long nbrCap = (long long)std::min<int64_t>(s.capPts, 0x7fffffff - MARK_LCAP);
   // the blocks stride over the keypoints with equal shares: a grid of exactly one resident wave
-  static int perSm = 0;
-  if (!perSm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_desc_mark, 256, MARK_LCAP * sizeof(unsigned)) != cudaSuccess) perSm = 4;
+  static const int perSm = []() {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_mark, 256, MARK_LCAP * sizeof(unsigned)) != cudaSuccess) v = 4;
+    return v;
+  }();
   gridKp = std::min(gridKp, 148 * std::max(perSm, 1));
   k_desc_mark<<<gridKp, 256, MARK_LCAP * sizeof(unsigned), s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted,
                                                                        surf_index(ctx, s), s.d_scan_off, P, s.d_rho, s.d_kpNbr,
