@@ -189,3 +189,21 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/fe_b200.h must compile as C99 and a C program must link
+    against the library (no C++ types or name mangling in the exported interface)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include <stdio.h>\n#include "fe_b200.h"\n'
+                   'int main(void) { fe_params_t p; fe_params_node_default(&p);\n'
+                   '  printf("%s %d %d\\n", fe_version(), (int)p.cluster_min_count, fe_device_count());\n'
+                   '  return fe_create(0, &p, NULL, NULL) == FE_OK; }\n')
+    exe = tmp_path / "c_abi"
+    libdir = os.path.join(root, "feature_extraction_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lfe_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and " 5 " in out.stdout, out.stdout + out.stderr
