@@ -406,6 +406,16 @@ def main():
         # the sample doubles as an in-bench parity check of the timed path
         same = bool(np.array_equal(ko[: n + 1], ko_o) and np.array_equal(kp[: ko[n]].view(np.uint32), kp_o.view(np.uint32)))
         out["parity_vs_oracle_on_sample"] = same
+        if same and d is not None and d_o is not None:
+            dg = d[: ko[n]]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                rel = np.abs(dg.astype(np.float64) - d_o) / np.maximum(np.abs(d_o), 1e-300)
+            rel = np.where((dg == d_o) | (np.isnan(dg) & np.isnan(d_o)), 0.0, rel)
+            rel = np.where(np.isnan(rel), np.inf, rel)
+            rows = rel.max(axis=1) if len(rel) else np.zeros(0)
+            out["descriptor_parity_on_sample"] = {
+                "keypoints": int(len(dg)), "rows_bit_identical": int((dg.view(np.uint32) == d_o.view(np.uint32)).all(axis=1).sum()),
+                "rows_beyond_1e-5": int((rows > 1e-5).sum()), "max_rel_err": float(rows.max()) if len(rows) else 0.0}
     if rank == 0:
         emit(out)
     host_node.close()

@@ -24,6 +24,7 @@ EXPORTS = [
     "fe_get_stage_times", "fe_enable_stage_timing", "fe_timer_begin", "fe_timer_end", "fe_get_batch_stats", "fe_get_elevation_angles", "fe_rotate_cloud", "fe_rotation_matrix",
     "fe_filter_cloud", "fe_extract_clusters", "fe_get_cylinder_segments", "fe_estimate_keypoints",
     "fe_estimate_descriptors", "fe_pack_point_descriptors",
+    "fe_set_angle_libm", "fe_enable_boundary_report", "fe_get_boundary_report",
 ]
 
 
@@ -130,5 +131,9 @@ def lib():
         L.fe_estimate_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.fe_pack_point_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.fe_debug_sort_replay.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.fe_set_angle_libm.argtypes = [C.c_void_p, C.c_int32]
+        L.fe_enable_boundary_report.argtypes = [C.c_void_p, C.c_double]
+        L.fe_get_boundary_report.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int32)]
+        L.fe_debug_libm_f32.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         _LIB = L
     return _LIB

@@ -46,6 +46,8 @@ struct Slot {
   float4 *d_kfPool = nullptr, *d_kcPool = nullptr, *d_kpPool = nullptr, *d_kpOut = nullptr, *d_gather = nullptr;
   float* d_desc = nullptr;
   DevCounters* d_ctr = nullptr;
+  unsigned long long* d_bnd = nullptr;  // tolerance-boundary report: [scan][4] pair counts
+  unsigned long long* h_bnd = nullptr;
   // pinned host mirrors
   long long* h_scan_off = nullptr;
   int* h_chunk_off = nullptr;
@@ -84,6 +86,9 @@ struct fe_ctx {
   bool cloudOutputs = false;
   bool stageTiming = false;   // serialise the stages and time each with CUDA events (fe_enable_stage_timing)
   bool recordOutput = false;  // descriptors leave as FE_RECORD_FLOATS-float PointDescriptor records
+  int angleLibm = 0;          // fe_set_angle_libm
+  double bndEps = 0.0;        // fe_enable_boundary_report: > 0 = count the pairs within bndEps of every radius
+  std::vector<int64_t> bndCounts;  // [scan][4] of the last batch call
   // results (host, pinned, grown on demand)
   std::vector<int64_t> kpOffsets;
   fe_point_t* h_kp = nullptr;
@@ -211,6 +216,7 @@ int derive_params(fe_ctx* ctx, const fe_params_t& p) {
   dp.R2f = radius_sq_as_flann_sees_it(p.descriptor_radius);
   dp.rho2f = radius_sq_as_flann_sees_it(p.descriptor_radius / 5.0);
   dp.estimate_descriptors = p.estimate_descriptors;
+  dp.angle_libm = ctx->angleLibm;
   std::vector<float> lut(FE_DESC_LEN);
   shape_context_tables(p.descriptor_radius, p.descriptor_radius / 10.0, dp.radii, dp.theta, dp.phi, lut.data());
   surface_grid(dp, p.descriptor_radius, dp.xmin, dp.xmax, dp.ymin, dp.ymax, dp.zmin, dp.zmax);
@@ -230,9 +236,9 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd};
   for (void* p : dv) if (p) cudaFree(p);
-  void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan};
+  void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd};
   for (void* p : hv) if (p) cudaFreeHost(p);
   for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
   if (s.evDone) cudaEventDestroy(s.evDone);
@@ -317,7 +323,11 @@ std::string err_bits(int e) {
 // the caller's array; the device sees offsets relative to the first point of the sub-batch.
 int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int nscans, int64_t* nptsOut, int* nchOut,
                 bool deferRot = false) {
+  // the pinned mirrors hold capScans(+1) entries: check before the first write
+  if (nscans > s.capScans) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_scans_per_call");
   const int64_t o0 = offs[0];
+  if (o0 < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must not be negative");
+  if (offs[nscans] - o0 > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_points_per_call");
   int nch = 0;
   for (int i = 0; i < nscans; i++) {
     const int64_t n = offs[i + 1] - offs[i];
@@ -333,8 +343,6 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
   s.h_chunk_off[nscans] = nch;
   *nptsOut = offs[nscans] - o0;
   *nchOut = nch;
-  if (*nptsOut > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_points_per_call");
-  if (nscans > s.capScans) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_scans_per_call");
   if (nch > s.capChunks) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds the chunk capacity");
   CK(cudaMemcpyAsync(s.d_scan_off, s.h_scan_off, (nscans + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_chunk_off, s.h_chunk_off, (nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
@@ -505,6 +513,27 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
 }
 
 
+// fe_enable_boundary_report: the four radius predicates of the path and the float pre-filter windows
+BoundarySpec boundary_spec(const fe_ctx* ctx) {
+  BoundarySpec B;
+  B.eps = ctx->bndEps;
+  const float r2[4] = {ctx->dp.r2f_cluster, ctx->dp.r2f_merge, ctx->dp.R2f, ctx->dp.rho2f};
+  for (int k = 0; k < 4; k++) {
+    B.r2f[k] = r2[k];
+    B.bdist[k] = sqrt((double)r2[k]);
+    B.win[k] = (float)(B.eps * (2.0 * B.bdist[k] + B.eps) * 1.01 + (double)r2[k] * 1e-6);
+  }
+  return B;
+}
+
+int ensure_bnd(fe_ctx* ctx, Slot& s) {
+  if (!s.d_bnd) {
+    CK(dalloc(&s.d_bnd, (size_t)s.capScans * 4));
+    CK(halloc(&s.h_bnd, (size_t)s.capScans * 4));
+  }
+  return FE_OK;
+}
+
 // Enqueue the kernels of one sub-batch whose points are at d_pts.  k1flags selects what K1 does;
 // `fromStage`: 0 = K1 first; 1 = crop/cropMeta/cropCnt already filled by the caller.
 int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int64_t npts, int nch,
@@ -544,6 +573,15 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     }
   }
   mark(ctx, s, "K1 level+crop+ring");
+  const bool bnd = ctx->bndEps > 0.0 && nscans > 0;
+  if (bnd) {
+    int st = ensure_bnd(ctx, s);
+    if (st) return st;
+    CK(cudaMemsetAsync(s.d_bnd, 0, (size_t)nscans * 4 * sizeof(unsigned long long), s.stream));
+    k_boundary_rings<<<nscans, 256, 0, s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, singleRing ? 1 : 0,
+                                                   boundary_spec(ctx), s.d_bnd);
+    ctx->launches++;
+  }
   s.sideK4a = false;
   if (doDesc) {
     int st = ensure_rowstart(ctx, s, nscans);
@@ -562,6 +600,10 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
   }
   launch_clustering(ctx, s, nscans, singleRing, wantKc, true, true);
   mark(ctx, s, "K3 merge keypoints");
+  if (bnd) {
+    k_boundary_merge<<<nscans, 128, 0, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, boundary_spec(ctx), s.d_bnd);
+    ctx->launches++;
+  }
   k_kp_offsets<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr);
   ctx->launches++;
   k_kp_gather<<<std::max(1, std::min(1024, (nscans * 8 + 255) / 256)), 256, 0, s.stream>>>(s.d_kpPool, s.d_kpBase, s.d_kpOff, nscans,
@@ -579,6 +621,14 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     const int gridKp = 148 * 8;
     launch_desc_mark(ctx, s, nscans, P, gridKp);
     mark(ctx, s, "K4b mark neighbours");
+    if (bnd) {  // before K4c turns the marks in rho into densities
+      k_boundary_support<<<148 * 4, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, surf_index(ctx, s),
+                                                         s.d_scan_off, P, boundary_spec(ctx), s.d_bnd);
+      if (npts > 0)
+        k_boundary_density<<<(int)std::min<int64_t>((npts + 255) / 256, 148 * 64), 256, 0, s.stream>>>(
+            s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, (long long)npts, s.d_rho, boundary_spec(ctx), s.d_bnd);
+      ctx->launches += 2;
+    }
     if (npts > 0) {
       const int gridD = (int)std::min<int64_t>((npts + 255) / 256, 148 * 64);
       k_density<<<gridD, 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, (long long)npts, s.d_rho);
@@ -590,6 +640,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
   }
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaMemcpyAsync(s.h_kpOff, s.d_kpOff, (size_t)(nscans + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  if (bnd) CK(cudaMemcpyAsync(s.h_bnd, s.d_bnd, (size_t)nscans * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaEventRecord(s.evDone, s.stream));
   CK(cudaGetLastError());
   return FE_OK;
@@ -638,6 +689,8 @@ int finalize_subbatch(fe_ctx* ctx, Slot& s, int64_t& kpRun, bool desc) {
   int st = grow_results(ctx, kpRun + K, desc);
   if (st) return st;
   for (int i = 0; i <= s.nscans; i++) ctx->kpOffsets[s.firstScan + i] = kpRun + s.h_kpOff[i];
+  if (ctx->bndEps > 0.0 && s.h_bnd)
+    for (int i = 0; i < s.nscans * 4; i++) ctx->bndCounts[(size_t)s.firstScan * 4 + i] = (int64_t)s.h_bnd[i];
   if (K > 0) {
     CK(cudaMemcpyAsync(ctx->h_kp + kpRun, s.d_kpOut, (size_t)K * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
     const size_t dl = ctx->recordOutput ? FE_RECORD_FLOATS : FE_DESC_LEN;
@@ -669,6 +722,24 @@ int gather_to_host(fe_ctx* ctx, Slot& s, int nscans, bool chunks, const float4* 
   CK(cudaStreamSynchronize(s.stream));
   return FE_OK;
 }
+
+// A host batch call that fails half-way leaves sub-batches in flight on the two slots.  Whatever the
+// exit path, both streams are drained and the slots marked idle, so the next call on the context starts
+// clean instead of finalising a stale sub-batch into its own result arrays.
+struct SlotDrain {
+  fe_ctx* ctx;
+  bool ok = false;
+  explicit SlotDrain(fe_ctx* c) : ctx(c) { drain(); }
+  ~SlotDrain() { if (!ok) drain(); }
+  void drain() {
+    for (int k = 0; k < 2; k++) {
+      Slot& s = ctx->slot[k];
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      if (s.stream2) cudaStreamSynchronize(s.stream2);
+      s.busy = false;
+    }
+  }
+};
 
 }  // namespace
 
@@ -803,6 +874,48 @@ int fe_enable_record_output(fe_ctx_t* ctx, int32_t enable) {
   return FE_OK;
 }
 
+int fe_set_angle_libm(fe_ctx_t* ctx, int32_t mode) {
+  if (!ctx || (mode != FE_LIBM_FDLIBM && mode != FE_LIBM_CORRECTLY_ROUNDED)) return FE_ERR_INVALID;
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+  ctx->angleLibm = mode;
+  ctx->dp.angle_libm = mode;
+  return FE_OK;
+}
+
+int fe_enable_boundary_report(fe_ctx_t* ctx, double eps_m) {
+  if (!ctx || !(eps_m == eps_m)) return FE_ERR_INVALID;
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+  ctx->bndEps = eps_m > 0.0 ? eps_m : 0.0;
+  ctx->bndCounts.clear();
+  return FE_OK;
+}
+
+int fe_get_boundary_report(fe_ctx_t* ctx, const int64_t** counts, int32_t* n_scans) {
+  if (!ctx || !counts || !n_scans) return FE_ERR_INVALID;
+  if (!(ctx->bndEps > 0.0)) return fail(ctx, FE_ERR_INVALID, "boundary report not enabled (fe_enable_boundary_report)");
+  *counts = ctx->bndCounts.data();
+  *n_scans = (int32_t)(ctx->bndCounts.size() / 4);
+  return FE_OK;
+}
+
+int fe_debug_libm_f32(fe_ctx_t* ctx, int32_t op, const float* a, const float* b, float* out, int64_t n) {
+  if (!ctx || op < 0 || op > 2 || n < 0 || (n > 0 && (!a || !out || (op == 0 && !b)))) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return FE_OK;
+  float *da = nullptr, *db = nullptr, *dout = nullptr;
+  auto done = [&](int code) { cudaFree(da); cudaFree(db); cudaFree(dout); return code; };
+  if (cudaMalloc((void**)&da, (size_t)n * 4) != cudaSuccess || cudaMalloc((void**)&db, (size_t)n * 4) != cudaSuccess ||
+      cudaMalloc((void**)&dout, (size_t)n * 4) != cudaSuccess)
+    return done(fail(ctx, FE_ERR_CUDA, "fe_debug_libm_f32: out of device memory"));
+  cudaMemcpy(da, a, (size_t)n * 4, cudaMemcpyHostToDevice);
+  if (op == 0) cudaMemcpy(db, b, (size_t)n * 4, cudaMemcpyHostToDevice);
+  k_debug_libm_f32<<<148 * 8, 256>>>(op, da, db, dout, (long long)n);
+  ctx->launches++;
+  if (cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return done(fail(ctx, FE_ERR_CUDA, std::string("fe_debug_libm_f32: ") + cudaGetErrorString(cudaGetLastError())));
+  return done(FE_OK);
+}
+
 int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_point_t** cloud,
                          const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud) {
   if (!ctx) return FE_ERR_INVALID;
@@ -815,7 +928,7 @@ int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_
 }
 
 int fe_get_stage_times(fe_ctx_t* ctx, int32_t cap, const char** names, float* ms, int32_t* n) {
-  if (!ctx || !n) return FE_ERR_INVALID;
+  if (!ctx || !n || cap < 0 || (cap > 0 && (!names || !ms))) return FE_ERR_INVALID;
   const int m = std::min<int>(cap, (int)ctx->stName.size());
   for (int i = 0; i < m; i++) { names[i] = ctx->stName[i]; ms[i] = ctx->stMs[i]; }
   *n = m;
@@ -829,9 +942,12 @@ static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int st
   if (!ctx || !out || n_scans < 0 || (n_scans > 0 && (!scan_offsets || !roll_pitch))) return FE_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   ctx->err.clear();
+  if (n_scans > 0 && scan_offsets[0] < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must not be negative");
+  SlotDrain guard(ctx);
   const bool desc = ctx->params.estimate_descriptors != 0;
   const int64_t launches0 = ctx->launches;
   ctx->kpOffsets.assign((size_t)n_scans + 1, 0);
+  ctx->bndCounts.assign(ctx->bndEps > 0.0 ? (size_t)n_scans * 4 : 0, 0);
   ctx->cloudOff.clear(); ctx->kcOff.clear(); ctx->cloudPts.clear(); ctx->kcPts.clear();
   int64_t kpRun = 0;
   int first = 0, cur = 0;
@@ -897,6 +1013,7 @@ static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int st
   out->descriptors = desc ? ctx->h_desc : nullptr;
   out->on_device = 0;
   out->gpu_launches = ctx->launches - launches0;
+  guard.ok = true;
   return FE_OK;
 }
 
@@ -950,6 +1067,7 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int
   if (!ctx || !out || n_scans < 0 || (n_scans > 0 && (!scan_offsets || !roll_pitch || !d_points))) return FE_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   ctx->err.clear();
+  if (n_scans > 0 && scan_offsets[0] < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must not be negative");
   const bool desc = ctx->params.estimate_descriptors != 0;
   const int64_t launches0 = ctx->launches;
   Slot& s = ctx->slot[0];
@@ -968,6 +1086,9 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int
     CK(cudaEventSynchronize(s.evDone));
     if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
     for (int i = 0; i <= n_scans; i++) ctx->kpOffsets[i] = s.h_kpOff[i];
+    ctx->bndCounts.assign(ctx->bndEps > 0.0 ? (size_t)n_scans * 4 : 0, 0);
+    if (ctx->bndEps > 0.0 && s.h_bnd)
+      for (int i = 0; i < n_scans * 4; i++) ctx->bndCounts[i] = (int64_t)s.h_bnd[i];
     collect_times(ctx, s);
     s.nscans = n_scans; s.npts = npts; s.lastNch = nch;
   }
@@ -1137,6 +1258,7 @@ int fe_extract_clusters(fe_ctx_t* ctx, const fe_point_t* cloud, int64_t n, doubl
   Slot& s = ctx->slot[0];
   int st = ensure_slot(ctx, s, true);
   if (st) return st;
+  if (n > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "fe_extract_clusters: more points than max_points_per_call");
   CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   const float tol_f = (float)tolerance;
   const float r2f = radius_sq_as_flann_sees_it((double)tol_f);

@@ -19,6 +19,7 @@
 #pragma once
 #include <math.h>
 #include "fe_device.cuh"
+#include "glibc_f32.h"
 #include "sort_replay.h"
 #include "../../include/fe_b200.h"
 
@@ -75,6 +76,7 @@ struct DevParams {
   float R2f, rho2f, Rpad, rhopad;
   float radii[16], theta[12], phi[13];
   int estimate_descriptors;
+  int angle_libm;  // 0: fdlibm atan2f/acosf (glibc <= 2.40), 1: correctly rounded (glibc >= 2.41)
 };
 
 struct DevCounters {
@@ -1622,8 +1624,12 @@ __device__ __forceinline__ bool shape_context_contribution(const float4 o, const
   const float crz = __fsub_rn(__fmul_rn(axx, pry), __fmul_rn(axy, prx));
   const float crn = __fsqrt_rn(eigen_sum3(__fmul_rn(crx, crx), __fmul_rn(cry, cry), __fmul_rn(crz, crz)));
   const float dt = eigen_sum3(__fmul_rn(axx, prx), __fmul_rn(axy, pry), __fmul_rn(axz, prz));
-  // atan2f / acosf through double so that the float result is (almost always) correctly rounded
-  float phi = __fmul_rn((float)atan2((double)crn, (double)dt), 57.29578f);
+  // std::atan2(float, float) / acosf: the host libm's float routines.  angle_libm 0 (default): the fdlibm
+  // algorithm of glibc <= 2.40, restated operation by operation (glibc_f32.h) — the same last bit as the
+  // reference's x86-64 build, so a neighbour on a bin edge lands in the same bin; 1: correctly rounded
+  // (evaluated in double, then narrowed), what glibc >= 2.41 (CORE-MATH) returns.
+  float phi = P.angle_libm ? (float)atan2((double)crn, (double)dt) : glibc::atan2f_fdlibm(crn, dt);
+  phi = __fmul_rn(phi, 57.29578f);
   const float cdn = eigen_sum3(__fmul_rn(crx, 0.0f), __fmul_rn(cry, 0.0f), __fmul_rn(crz, 1.0f));
   phi = (cdn < 0.f) ? __fsub_rn(360.0f, phi) : phi;
   float nox = pox, noy = poy, noz = poz;
@@ -1634,7 +1640,7 @@ __device__ __forceinline__ bool shape_context_contribution(const float4 o, const
   float th = eigen_sum3(__fmul_rn(0.0f, nox), __fmul_rn(0.0f, noy), __fmul_rn(1.0f, noz));
   const float t1 = (-1.0f < th) ? th : -1.0f;  // std::max(-1.0f, theta)
   const float t2 = (t1 < 1.0f) ? t1 : 1.0f;    // std::min(1.0f, .)
-  th = __fmul_rn((float)acos((double)t2), 57.29578f);
+  th = __fmul_rn(P.angle_libm ? (float)acos((double)t2) : glibc::acosf_fdlibm(t2), 57.29578f);
   int j = 0, k = 0, l = 0;
 #pragma unroll
   for (int a = 15; a >= 1; a--) if (rr <= P.radii[a]) j = a - 1;
@@ -1881,6 +1887,181 @@ __global__ void __launch_bounds__(256) k_record_frame(const float4* __restrict__
     if (f < 5) r[f] = (f == 0) ? k.x : (f == 1) ? k.y : (f == 2) ? k.z : (f == 3) ? 0.0f : k.w;
     else r[5 + descLen + (f - 5)] = 0.0f;
   }
+}
+
+// ============================================================================================
+// Tolerance-boundary report (fe_enable_boundary_report) — audit kernels, not part of the hot path.
+// BASELINE.json north_star: "points lying within 1e-6 m of a tolerance boundary reported
+// separately".  Every radius predicate of the path is d2 < r2f in float; a pair is on the boundary
+// when |sqrt((double)d2) - sqrt((double)r2f)| < eps.  bnd[4*scan + k] counts them per predicate:
+//   0 ring clustering (src:269-276): unordered pairs of crop points sharing a ring
+//   1 cross-ring merge (src:222-229): unordered pairs of ring centroids (pseudo z, src:217)
+//   2 3DSC support radius (src:350): (keypoint, surface point) pairs
+//   3 3DSC point-density radius (src:352): (marked surface point, surface point) pairs, the query
+//     being every surface point inside some keypoint's sphere, once
+// The oracle counts the same pairs in its own searches (feo_process_batch_boundary).
+// ============================================================================================
+struct BoundarySpec {
+  double eps;
+  double bdist[4];  // sqrt((double)r2f) of the four predicates
+  float r2f[4];
+  float win[4];     // float pre-filter on |d2 - r2f| that contains every boundary pair
+};
+
+__device__ __forceinline__ bool on_boundary(const BoundarySpec& B, int k, float d2) {
+  if (!(fabsf(d2 - B.r2f[k]) <= B.win[k])) return false;
+  return fabs(sqrt((double)d2) - B.bdist[k]) < B.eps;
+}
+
+constexpr int BND_TILE = 1024;
+
+// one block per scan: all pairs of the scan's crop survivors (tiles of BND_TILE in shared memory)
+__global__ void __launch_bounds__(256) k_boundary_rings(
+    const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta, const int* __restrict__ cropCnt,
+    const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, int single_ring, BoundarySpec B,
+    unsigned long long* __restrict__ bnd) {
+  __shared__ int pre[MAXCHUNK + 1];
+  __shared__ int sc[40];
+  __shared__ float4 tile[BND_TILE];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const long long base = scan_off[s];
+  const int nch = chunk_off[s + 1] - chunk_off[s];
+  if (nch > MAXCHUNK) return;
+  const int Nc = chunk_prefix<256>(cropCnt + chunk_off[s], nch, pre, sc);
+  unsigned long long cnt = 0;
+  auto ring_mask = [&](unsigned cd) -> unsigned {
+    if (cd & 32u) return 0u;
+    if (single_ring) return 1u;
+    const unsigned r = cd & 15u;
+    return (1u << r) | ((cd & 16u) ? (1u << (r + 1)) : 0u);
+  };
+  for (int t0 = 0; t0 < Nc; t0 += BND_TILE) {
+    __syncthreads();
+    for (int j = tid; j < BND_TILE && t0 + j < Nc; j += 256) {
+      const long long pp = piece_pos(pre, nch, t0 + j, base);
+      float4 q = crop[pp];
+      q.w = __uint_as_float(ring_mask(cropMeta[pp] & 63u));
+      tile[j] = q;
+    }
+    __syncthreads();
+    const int tn = min(BND_TILE, Nc - t0);
+    for (int i = tid; i < t0 + tn; i += 256) {  // i < j, j inside the tile
+      float4 p;
+      if (i >= t0) p = tile[i - t0];
+      else {
+        const long long pp = piece_pos(pre, nch, i, base);
+        p = crop[pp];
+        p.w = __uint_as_float(ring_mask(cropMeta[pp] & 63u));
+      }
+      const unsigned mi = __float_as_uint(p.w);
+      if (!mi) continue;
+      for (int j = max(i + 1 - t0, 0); j < tn; j++) {
+        const float4 q = tile[j];
+        const unsigned both = mi & __float_as_uint(q.w);
+        if (!both) continue;
+        if (on_boundary(B, 0, l2_simple(p.x, p.y, p.z, q.x, q.y, q.z))) cnt += (unsigned)__popc(both);
+      }
+    }
+  }
+  if (cnt) atomicAdd(&bnd[4 * s + 0], cnt);
+}
+
+// one block per scan: all pairs of the scan's ring centroids with the pseudo z of src:217
+__global__ void __launch_bounds__(128) k_boundary_merge(const float4* __restrict__ kfPool, const int* __restrict__ kfBase,
+                                                        const int* __restrict__ kfCnt, DevParams P, BoundarySpec B,
+                                                        unsigned long long* __restrict__ bnd) {
+  __shared__ int pre[17];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    int run = 0;
+    for (int g = 0; g < 16; g++) { pre[g] = run; run += kfCnt[s * 16 + g]; }
+    pre[16] = run;
+  }
+  __syncthreads();
+  const int Kf = pre[16];
+  auto load = [&](int i) -> float4 {
+    int g = 0;
+    while (g < 15 && pre[g + 1] <= i) g++;
+    float4 q = kfPool[kfBase[s * 16 + g] + (i - pre[g])];
+    q.z = (float)__ddiv_rn(__dmul_rn(__dmul_rn((double)q.w, 0.75), P.radius_threshold), 2.0);
+    return q;
+  };
+  unsigned long long cnt = 0;
+  for (int i = tid; i < Kf; i += 128) {
+    const float4 p = load(i);
+    for (int j = i + 1; j < Kf; j++) {
+      const float4 q = load(j);
+      if (on_boundary(B, 1, l2_simple(p.x, p.y, p.z, q.x, q.y, q.z))) cnt++;
+    }
+  }
+  if (cnt) atomicAdd(&bnd[4 * s + 1], cnt);
+}
+
+// keypoints against the search surface (slot 2): the sweep of K4b, widened by eps
+__global__ void __launch_bounds__(256) k_boundary_support(
+    const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff, int n_scans,
+    const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P, BoundarySpec B,
+    unsigned long long* __restrict__ bnd) {
+  const int total = kpOff[n_scans];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    const float4 o = kpOut[g];
+    const int s = kpScan[g];
+    if (!finite3(o.x, o.y, o.z)) continue;
+    const long long base = scan_off[s];
+    const float4* so = sorted + base;
+    const unsigned* sk = X.sortedKey + base;
+    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+    const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
+    const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
+    unsigned long long cnt = 0;
+    for (int r = cy0 + w; r <= cy1; r += 8) {
+      int b, e;
+      row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
+      for (int i = b + lane; i < e; i += 32) {
+        const float4 q = so[i];
+        if (on_boundary(B, 2, l2_simple(o.x, o.y, o.z, q.x, q.y, q.z))) cnt++;
+      }
+    }
+    if (cnt) atomicAdd(&bnd[4 * s + 2], cnt);
+  }
+}
+
+// marked surface points against the surface (slot 3): the sweep of K4c; runs while rho still holds
+// the marks -(scan+1) that K4b left
+__global__ void __launch_bounds__(256) k_boundary_density(
+    const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P, long long total,
+    const int* __restrict__ rho, BoundarySpec B, unsigned long long* __restrict__ bnd) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = rho[i];
+    if (v >= 0) continue;
+    const int s = -v - 1;
+    const long long base = scan_off[s];
+    const float4* so = sorted + base;
+    const unsigned* sk = X.sortedKey + base;
+    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+    const float4 p = sorted[i];
+    const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, P.sg_nx);
+    const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, P.sg_ny);
+    unsigned long long cnt = 0;
+    for (int r = cy0; r <= cy1; r++) {
+      int b, e;
+      row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
+      for (int j = b; j < e; j++) {
+        const float4 q = so[j];
+        if (on_boundary(B, 3, l2_simple(p.x, p.y, p.z, q.x, q.y, q.z))) cnt++;
+      }
+    }
+    if (cnt) atomicAdd(&bnd[4 * s + 3], cnt);
+  }
+}
+
+// test hook: the device's fdlibm restatement (glibc_f32.h) element-wise; op 0 atan2f(a,b), 1 acosf(a), 2 atanf(a)
+__global__ void k_debug_libm_f32(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = op == 0 ? glibc::atan2f_fdlibm(a[i], b[i]) : op == 1 ? glibc::acosf_fdlibm(a[i]) : glibc::atanf_fdlibm(a[i]);
 }
 
 }  // namespace fe

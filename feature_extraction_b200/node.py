@@ -46,6 +46,22 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _batch_args(n_records, scan_offsets, roll_pitch):
+    """Validate a CSR batch before raw pointers cross the C-ABI (the library trusts its caller's sizes)."""
+    offs = np.ascontiguousarray(scan_offsets, np.int64).reshape(-1)
+    if len(offs) < 1:
+        raise ValueError("scan_offsets needs n_scans + 1 entries")
+    B = len(offs) - 1
+    rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
+    if len(rp) != 2 * B:
+        raise ValueError("roll_pitch needs 2 values per scan: got %d for %d scans" % (len(rp), B))
+    if offs[0] < 0 or np.any(np.diff(offs) < 0):
+        raise ValueError("scan_offsets must start at >= 0 and be non-decreasing")
+    if n_records is not None and offs[-1] > n_records:
+        raise ValueError("scan_offsets[-1] = %d exceeds the %d records passed" % (offs[-1], n_records))
+    return offs, rp, B
+
+
 class PinnedBuffer:
     """Page-locked host memory from fe_host_alloc, exposed as a numpy array."""
 
@@ -202,9 +218,7 @@ class FeatureExtractionNode:
         """fe_process_batch_layout: `raw` is a contiguous uint8/any-dtype host buffer of records."""
         buf = np.ascontiguousarray(raw)
         lay = N.PointLayout(int(stride), int(x_off), int(y_off), int(z_off))
-        offs = np.ascontiguousarray(scan_offsets, np.int64)
-        rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
-        B = len(offs) - 1
+        offs, rp, B = _batch_args(buf.nbytes // max(int(stride), 1), scan_offsets, roll_pitch)
         res = N.BatchResult()
         self._check(N.lib().fe_process_batch_layout(self._ctx, _ptr(buf), C.byref(lay), _ptr(offs), _ptr(rp), B, C.byref(res)))
         return self._unpack(res, B, copy)
@@ -216,9 +230,7 @@ class FeatureExtractionNode:
         With copy=False the arrays alias context-owned pinned memory (valid until the next call).
         """
         c = _cloud(points)
-        offs = np.ascontiguousarray(scan_offsets, np.int64)
-        rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
-        B = len(offs) - 1
+        offs, rp, B = _batch_args(len(c), scan_offsets, roll_pitch)
         res = N.BatchResult()
         self._check(N.lib().fe_process_batch(self._ctx, _ptr(c), _ptr(offs), _ptr(rp), B, C.byref(res)))
         return self._unpack(res, B, copy)
@@ -252,9 +264,7 @@ class FeatureExtractionNode:
 
         -> keypoint_offsets (B+1,) int64 host copy, n_keypoints, device ptr keypoints, device ptr descriptors
         """
-        offs = np.ascontiguousarray(scan_offsets, np.int64)
-        rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
-        B = len(offs) - 1
+        offs, rp, B = _batch_args(None, scan_offsets, roll_pitch)  # the device buffer's size is the caller's business
         res = N.BatchResult()
         self._check(N.lib().fe_process_batch_device(self._ctx, C.c_void_p(d_points_ptr), _ptr(offs), _ptr(rp), B, C.byref(res)))
         self.last_launches = int(res.gpu_launches)
@@ -284,6 +294,31 @@ class FeatureExtractionNode:
                 return np.zeros((0, 4), np.float32)
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, 4)).copy()
         return co, arr(cp, int(co[-1])), kco, arr(kcp, int(kco[-1]))
+
+    def setAngleLibm(self, correctly_rounded=False):
+        """fe_set_angle_libm: fdlibm atan2f/acosf (glibc <= 2.40, default) or correctly rounded (>= 2.41)."""
+        self._check(N.lib().fe_set_angle_libm(self._ctx, 1 if correctly_rounded else 0))
+
+    def enableBoundaryReport(self, eps_m=1e-6):
+        """fe_enable_boundary_report: count, per scan, the pairs within eps_m of every radius predicate."""
+        self._check(N.lib().fe_enable_boundary_report(self._ctx, float(eps_m)))
+
+    def boundaryReport(self):
+        """-> (n_scans, 4) int64: ring clustering, cross-ring merge, 3DSC support, 3DSC density."""
+        p = C.POINTER(C.c_int64)()
+        n = C.c_int32(0)
+        self._check(N.lib().fe_get_boundary_report(self._ctx, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, 4), np.int64)
+        return np.ctypeslib.as_array(p, shape=(n.value, 4)).copy()
+
+    def debugLibm(self, op, a, b=None):
+        """Test hook: the device's atan2f (op 0), acosf (1), atanf (2) element-wise."""
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b if b is not None else a, np.float32)
+        out = np.empty_like(a)
+        self._check(N.lib().fe_debug_libm_f32(self._ctx, int(op), _ptr(a), _ptr(b), _ptr(out), a.size))
+        return out
 
     def timerBegin(self):
         self._check(N.lib().fe_timer_begin(self._ctx))
@@ -348,9 +383,7 @@ class MultiGpuExtractor:
 
     def processBatch(self, points, scan_offsets, roll_pitch, copy=True):
         c = _cloud(points)
-        offs = np.ascontiguousarray(scan_offsets, np.int64)
-        rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
-        B = len(offs) - 1
+        offs, rp, B = _batch_args(len(c), scan_offsets, roll_pitch)
         res = N.BatchResult()
         st = N.lib().fe_multi_process_batch(self._m, _ptr(c), _ptr(offs), _ptr(rp), B, C.byref(res))
         if st != N.FE_OK:

@@ -161,9 +161,38 @@ int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_
  * records of FE_RECORD_FLOATS floats in the layout of pcl::PointDescriptor
  * (feature_extraction_node.h:35-53): x, y, z, 0 | intensity | descriptor[1980] | rf[9] = 0 | padding —
  * what fe_pack_point_descriptors() would build on the host, ready to be published as ~features.
- * `keypoints` is filled as before.  Needs estimate_descriptors != 0. */
+ * `keypoints` is filled as before.  With estimate_descriptors == 0 there are no descriptors and hence no
+ * records (the reference publishes ~features only inside `if (descriptorEstimation)`, src:112-124): the
+ * setting is kept but has no effect. */
 int fe_enable_record_output(fe_ctx_t* ctx, int32_t enable);
 int fe_multi_enable_record_output(fe_multi_t* m, int32_t enable);
+
+/* Which float libm the 3DSC angles follow.  pcl::ShapeContext3DEstimation::computePoint (3dsc.hpp,
+ * called at src:353) bins a neighbour by rad2deg(atan2(float, float)) and rad2deg(acosf(float)), i.e. by
+ * the last bit of the host libm's atan2f / acosf.  FE_LIBM_FDLIBM (default): the fdlibm float routines
+ * of glibc <= 2.40 restated on the device operation by operation (csrc/glibc_f32.h) — bit-identical to
+ * the reference's x86-64 build and to this image's glibc 2.39.  FE_LIBM_CORRECTLY_ROUNDED: what
+ * glibc >= 2.41 (CORE-MATH) returns. */
+#define FE_LIBM_FDLIBM 0
+#define FE_LIBM_CORRECTLY_ROUNDED 1
+int fe_set_angle_libm(fe_ctx_t* ctx, int32_t mode);
+
+/* Tolerance-boundary report (BASELINE.json north_star: "points lying within 1e-6 m of a tolerance
+ * boundary reported separately").  Every radius predicate of the path is d2 < r2f evaluated in float
+ * (FLANN L2_Simple; r2f = (float)(radius*radius)); a point pair is ON THE BOUNDARY of a predicate when
+ * |sqrt((double)d2) - sqrt((double)r2f)| < eps_m.  After fe_enable_boundary_report(ctx, eps_m > 0) every
+ * batch call also counts those pairs per scan — audit kernels next to the pipeline, slower — and
+ * fe_get_boundary_report returns n_scans x 4 counts of the last call:
+ *   [0] ring clustering, src:269-276: unordered pairs of cropped points of one ring (a point on a ring
+ *       window's end value belongs to two rings, src:200-202, and counts in both)
+ *   [1] cross-ring merge, src:222-229: unordered pairs of ring centroids with the pseudo z of src:217
+ *   [2] 3DSC support radius, src:350: (keypoint, surface point) pairs
+ *   [3] 3DSC point-density radius, src:352: (neighbour, surface point) pairs, the neighbour being every
+ *       surface point inside some keypoint's support sphere, counted once
+ * A scan with all four counts 0 has no decision within eps_m of flipping; the CPU oracle counts the same
+ * pairs (feo_process_batch_boundary) and tools/parity_campaign.py prints both.  eps_m <= 0 disables. */
+int fe_enable_boundary_report(fe_ctx_t* ctx, double eps_m);
+int fe_get_boundary_report(fe_ctx_t* ctx, const int64_t** counts, int32_t* n_scans);
 
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of
  * fe_process_batch_device is launched on): begin, run any number of calls, end -> elapsed ms. */

@@ -161,6 +161,17 @@ inline float l2_simple(const P4& a, const P4& b) {
 // KdTreeFLANN::radiusSearch: static_cast<float>(radius * radius), radius a double.
 inline float radius_sq_float(double radius) { return (float)(radius * radius); }
 
+// Tolerance-boundary report (BASELINE.json north_star: "points lying within 1e-6 m of a tolerance
+// boundary reported separately").  Every radius predicate of the path is d2 < r2f in float; a pair is
+// "on the boundary" when |sqrt((double)d2) - sqrt((double)r2f)| < eps.  Slots: 0 ring clustering
+// (src:269-276), 1 cross-ring merge (src:222-229), 2 3DSC support radius (src:350), 3 3DSC point
+// density radius (src:352).  The product counts the same pairs with its own kernels
+// (fe_enable_boundary_report); the two must agree.
+struct BoundaryCounter {
+  double eps = 0.0;
+  int64_t n[4] = {0, 0, 0, 0};
+};
+
 struct Hit { float d2; int idx; };
 inline bool hit_less(const Hit& a, const Hit& b) {  // flann::DistanceIndex::operator<
   return (a.d2 < b.d2) || ((a.d2 == b.d2) && a.idx < b.idx);
@@ -175,6 +186,9 @@ struct Searcher {
   struct Node { float lo[3], hi[3]; int left, right, begin, end; };
   std::vector<Node> nodes;
   std::vector<int> order;
+  // boundary report: pairs (query, point) evaluated by radius() whose distance is within eps of the radius
+  double bnd_eps = 0.0;
+  mutable int64_t bnd_hits = 0;
 
   void set_input(const P4* p, int n_, bool tree, bool sorted_) {
     pts = p; n = n_; use_tree = tree; sorted = sorted_;
@@ -222,10 +236,14 @@ struct Searcher {
   // all j with l2_simple(q, pts[j]) < r2f; returns count
   int radius(const P4& q, float r2f, std::vector<Hit>& out) const {
     out.clear();
+    const bool bnd = bnd_eps > 0.0;
+    const double bdist = bnd ? sqrt((double)r2f) : 0.0;
+    const double r2prune = bnd ? (bdist + 2.0 * bnd_eps) * (bdist + 2.0 * bnd_eps) : (double)r2f;
     if (!use_tree) {
       for (int j = 0; j < n; j++) {
         float d2 = l2_simple(q, pts[j]);
         if (d2 < r2f) out.push_back({d2, j});
+        if (bnd && fabs(sqrt((double)d2) - bdist) < bnd_eps) bnd_hits++;
       }
     } else if (!nodes.empty()) {
       int stack[128]; int sp = 0; stack[sp++] = 0;
@@ -237,12 +255,13 @@ struct Searcher {
           if (v < nd.lo[d]) t = (double)nd.lo[d] - v; else if (v > nd.hi[d]) t = v - (double)nd.hi[d];
           lb += t * t;
         }
-        if (lb * (1.0 - 1e-6) >= (double)r2f) continue;
+        if (lb * (1.0 - 1e-6) >= r2prune) continue;
         if (nd.left < 0) {
           for (int i = nd.begin; i < nd.end; i++) {
             int j = order[i];
             float d2 = l2_simple(q, pts[j]);
             if (d2 < r2f) out.push_back({d2, j});
+            if (bnd && fabs(sqrt((double)d2) - bdist) < bnd_eps) bnd_hits++;
           }
         } else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
       }
@@ -265,7 +284,8 @@ bool compare_point_clusters(const std::vector<int>& a, const std::vector<int>& b
 }
 
 void euclidean_cluster_extract(const std::vector<P4>& cloud, double tolerance_d, int min_size,
-                               int max_size, bool use_tree, Clusters& clusters) {
+                               int max_size, bool use_tree, Clusters& clusters,
+                               BoundaryCounter* bc = nullptr, int bslot = 0) {
   clusters.clear();
   const int n = (int)cloud.size();
   if (n == 0) return;
@@ -273,6 +293,7 @@ void euclidean_cluster_extract(const std::vector<P4>& cloud, double tolerance_d,
   const float r2f = radius_sq_float((double)tolerance);  // radiusSearch(.., double radius, ..)
   Searcher tree;
   tree.set_input(cloud.data(), n, use_tree, /*sorted=*/false);  // search::KdTree<PointT>(false)
+  if (bc) tree.bnd_eps = bc->eps;
   std::vector<char> processed(n, 0);
   std::vector<Hit> nn;
   std::vector<int> seed_queue;
@@ -299,6 +320,8 @@ void euclidean_cluster_extract(const std::vector<P4>& cloud, double tolerance_d,
     }
   }
   std::sort(clusters.rbegin(), clusters.rend(), compare_point_clusters);
+  // every point is the query of exactly one search, so each unordered pair was seen twice
+  if (bc) bc->n[bslot] += tree.bnd_hits / 2;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -306,11 +329,11 @@ void euclidean_cluster_extract(const std::vector<P4>& cloud, double tolerance_d,
 // ------------------------------------------------------------------------------------------
 void get_cylinder_segments(const fe_params_t& P, const std::vector<P4>& cloud, bool use_tree,
                            std::vector<P4>& keypoints, std::vector<P4>& keypoint_cloud,
-                           Clusters* clusters_out = nullptr) {
+                           Clusters* clusters_out = nullptr, BoundaryCounter* bc = nullptr) {
   if (cloud.size() <= 0) return;  // src:263-264
   Clusters clusterIndices;
   euclidean_cluster_extract(cloud, P.cluster_tolerance, P.cluster_min_count, P.cluster_max_count,
-                            use_tree, clusterIndices);  // src:269-276
+                            use_tree, clusterIndices, bc, 0);  // src:269-276
   if (clusters_out) *clusters_out = clusterIndices;
   if (clusterIndices.size() <= 0) return;  // src:278-279
   for (size_t i = 0; i < clusterIndices.size(); ++i) {
@@ -350,14 +373,14 @@ void get_cylinder_segments(const fe_params_t& P, const std::vector<P4>& cloud, b
 // ------------------------------------------------------------------------------------------
 void estimate_keypoints(const fe_params_t& P, const std::vector<P4>& cloud, bool use_tree,
                         std::vector<P4>& keypoints, std::vector<P4>& keypoint_cloud,
-                        std::vector<P4>* keypoints_full_out = nullptr) {
+                        std::vector<P4>* keypoints_full_out = nullptr, BoundaryCounter* bc = nullptr) {
   std::vector<P4> keypoints_full;
   double channelElevationDegrees;
   for (int i = 0; i < 16; ++i) {  // src:195
     std::vector<P4> cylinderCentroids, cylinderCloud, channel;
     channelElevationDegrees = (i - 7) * 2 - 1;  // src:200
     pass_through(cloud, FI, channelElevationDegrees - 1.0, channelElevationDegrees + 1.0, channel);
-    get_cylinder_segments(P, channel, use_tree, cylinderCentroids, cylinderCloud);
+    get_cylinder_segments(P, channel, use_tree, cylinderCentroids, cylinderCloud, nullptr, bc);
     keypoints_full.insert(keypoints_full.end(), cylinderCentroids.begin(), cylinderCentroids.end());
     keypoint_cloud.insert(keypoint_cloud.end(), cylinderCloud.begin(), cylinderCloud.end());
   }
@@ -371,7 +394,7 @@ void estimate_keypoints(const fe_params_t& P, const std::vector<P4>& cloud, bool
   }
   Clusters clusterIndices;
   euclidean_cluster_extract(keypoints_full, P.cluster_radius_threshold, P.number_detection_channels,
-                            16, use_tree, clusterIndices);  // src:222-229
+                            16, use_tree, clusterIndices, bc, 1);  // src:222-229
   for (size_t i = 0; i < keypoints_full.size(); ++i) keypoints_full[i].z = (float)zhold[i];  // src:231-232
   if (clusterIndices.size() <= 0) return;  // src:234-235
 
@@ -452,7 +475,7 @@ struct DescDebug {      // per keypoint, optional
 // estimateDescriptors, src:329-355.  `desc` is K x 1980.
 void estimate_descriptors(const fe_params_t& P, const std::vector<P4>& cloud,
                           const std::vector<P4>& keypoints, bool use_tree, float* desc,
-                          DescDebug* dbg = nullptr) {
+                          DescDebug* dbg = nullptr, BoundaryCounter* bc = nullptr) {
   if (keypoints.size() <= 0) return;  // src:331-332
   const V3 normal_const = v3(0.0f, 0.0f, 1.0f);  // src:337-340, every surface normal
   const double search_radius = P.descriptor_radius;          // src:350
@@ -473,6 +496,9 @@ void estimate_descriptors(const fe_params_t& P, const std::vector<P4>& cloud,
   std::vector<Hit> nn, nn2;
   std::vector<int> rho_cache;  // density depends only on the surface point; cached in brute mode
   if (!use_tree) rho_cache.assign(cloud.size(), -1);
+  // boundary report: the density search of a surface point is counted once, however many keypoints reach it
+  std::vector<char> rho_counted;
+  if (bc) rho_counted.assign(cloud.size(), 0);
 
   for (size_t kp = 0; kp < keypoints.size(); kp++) {
     float* d = desc + kp * FE_DESC_LEN;
@@ -482,7 +508,9 @@ void estimate_descriptors(const fe_params_t& P, const std::vector<P4>& cloud,
       for (int i = 0; i < FE_DESC_LEN; i++) d[i] = std::numeric_limits<float>::quiet_NaN();
       continue;
     }
+    if (bc) { tree.bnd_eps = bc->eps; tree.bnd_hits = 0; }
     const size_t neighb_cnt = (size_t)tree.radius(in, R2f, nn);
+    if (bc) { bc->n[2] += tree.bnd_hits; tree.bnd_eps = 0.0; }
     if (neighb_cnt == 0) {
       for (int i = 0; i < FE_DESC_LEN; i++) d[i] = std::numeric_limits<float>::quiet_NaN();
       continue;
@@ -504,6 +532,13 @@ void estimate_descriptors(const fe_params_t& P, const std::vector<P4>& cloud,
     eigen32_normalize(x_axis);
 
     for (size_t ne = 0; ne < neighb_cnt; ne++) {
+      if (bc && !rho_counted[nn[ne].idx]) {  // boundary report only: a search of its own, once per surface point
+        rho_counted[nn[ne].idx] = 1;
+        tree.bnd_eps = bc->eps; tree.bnd_hits = 0;
+        tree.radius(cloud[nn[ne].idx], rho2f, nn2);
+        bc->n[3] += tree.bnd_hits;
+        tree.bnd_eps = 0.0;
+      }
       if (pcl_utils_equal(nn[ne].d2, 0.0f)) continue;
       const P4& nbp = cloud[nn[ne].idx];
       const V3 neighbour = v3(nbp.x, nbp.y, nbp.z);
@@ -555,23 +590,27 @@ struct ScanResult {
   std::vector<P4> cloud_full, cloud, keypoints, keypoint_cloud;
   std::vector<float> descriptors;
   std::vector<DescDebug> dbg;
+  BoundaryCounter bnd;
 };
 
 void process_scan(const fe_params_t& P, const P4* pts, int64_t n, double roll, double pitch,
-                  bool use_tree, bool want_dbg, ScanResult& R) {
+                  bool use_tree, bool want_dbg, ScanResult& R, double boundary_eps = 0.0) {
+  R.bnd = BoundaryCounter();
+  R.bnd.eps = boundary_eps;
+  BoundaryCounter* bc = boundary_eps > 0.0 ? &R.bnd : nullptr;
   R.cloud_full.assign(pts, pts + n);
   get_elevation_angles(R.cloud_full.data(), n);      // src:87
   rotate_cloud(R.cloud_full.data(), n, roll, pitch); // src:92
   R.cloud = R.cloud_full;                            // src:98
   filter_cloud(P, R.cloud);                          // src:99
   R.keypoints.clear(); R.keypoint_cloud.clear();
-  estimate_keypoints(P, R.cloud, use_tree, R.keypoints, R.keypoint_cloud);  // src:107
+  estimate_keypoints(P, R.cloud, use_tree, R.keypoints, R.keypoint_cloud, nullptr, bc);  // src:107
   R.descriptors.clear(); R.dbg.clear();
   if (P.estimate_descriptors) {  // src:112
     R.descriptors.assign(R.keypoints.size() * (size_t)FE_DESC_LEN, 0.0f);
     if (want_dbg) R.dbg.resize(R.keypoints.size());
     estimate_descriptors(P, R.cloud_full, R.keypoints, use_tree, R.descriptors.data(),
-                         want_dbg ? R.dbg.data() : nullptr);  // src:115
+                         want_dbg ? R.dbg.data() : nullptr, bc);  // src:115
   }
 }
 
@@ -781,10 +820,11 @@ int feo_process_scan(const fe_params_t* P, const fe_point_t* points, int64_t n, 
 // one scan at a time in ros::spin, src:386).  keypoint_offsets has n_scans+1 entries.
 // descriptors (nullable) must hold cap_kp * 1980 floats.  Returns FE_ERR_CAPACITY on overflow
 // (n_kp_total is still set to the required total).
-int feo_process_batch(const fe_params_t* P, const fe_point_t* points, const int64_t* scan_offsets,
+static int process_batch_impl(const fe_params_t* P, const fe_point_t* points, const int64_t* scan_offsets,
                       const double* roll_pitch, int32_t n_scans, int32_t mode, int32_t n_threads,
                       int64_t* keypoint_offsets, fe_point_t* keypoints, float* descriptors,
-                      float* edge_margin, int64_t cap_kp, int64_t* n_kp_total) {
+                      float* edge_margin, int64_t cap_kp, int64_t* n_kp_total,
+                      double boundary_eps, int64_t* boundary_counts) {
   std::vector<ScanResult> res(n_scans);
   if (n_threads < 1) n_threads = 1;
   std::atomic<int> next(0);
@@ -793,7 +833,8 @@ int feo_process_batch(const fe_params_t* P, const fe_point_t* points, const int6
       int s = next.fetch_add(1);
       if (s >= n_scans) break;
       process_scan(*P, points + scan_offsets[s], scan_offsets[s + 1] - scan_offsets[s],
-                   roll_pitch[2 * s], roll_pitch[2 * s + 1], mode == 1, edge_margin != nullptr, res[s]);
+                   roll_pitch[2 * s], roll_pitch[2 * s + 1], mode == 1, edge_margin != nullptr, res[s],
+                   boundary_counts ? boundary_eps : 0.0);
       res[s].cloud_full.clear(); res[s].cloud_full.shrink_to_fit();
       res[s].cloud.clear(); res[s].cloud.shrink_to_fit();
       res[s].keypoint_cloud.clear();
@@ -812,6 +853,9 @@ int feo_process_batch(const fe_params_t* P, const fe_point_t* points, const int6
     if (keypoint_offsets) keypoint_offsets[s + 1] = total;
   }
   if (n_kp_total) *n_kp_total = total;
+  if (boundary_counts)
+    for (int s = 0; s < n_scans; s++)
+      for (int k = 0; k < 4; k++) boundary_counts[4 * s + k] = res[s].bnd.n[k];
   if (!keypoints) return FE_OK;
   if (total > cap_kp) return FE_ERR_CAPACITY;
   int64_t t = 0;
@@ -825,6 +869,33 @@ int feo_process_batch(const fe_params_t* P, const fe_point_t* points, const int6
     t += (int64_t)k;
   }
   return FE_OK;
+}
+
+int feo_process_batch(const fe_params_t* P, const fe_point_t* points, const int64_t* scan_offsets,
+                      const double* roll_pitch, int32_t n_scans, int32_t mode, int32_t n_threads,
+                      int64_t* keypoint_offsets, fe_point_t* keypoints, float* descriptors,
+                      float* edge_margin, int64_t cap_kp, int64_t* n_kp_total) {
+  return process_batch_impl(P, points, scan_offsets, roll_pitch, n_scans, mode, n_threads, keypoint_offsets, keypoints,
+                            descriptors, edge_margin, cap_kp, n_kp_total, 0.0, nullptr);
+}
+
+// The same batch with the tolerance-boundary report: boundary_counts[4*s + k] = pairs of scan s within
+// eps_m of the radius of predicate k (0 ring clustering, 1 cross-ring merge, 2 3DSC support radius,
+// 3 3DSC point-density radius).
+int feo_process_batch_boundary(const fe_params_t* P, const fe_point_t* points, const int64_t* scan_offsets,
+                               const double* roll_pitch, int32_t n_scans, int32_t mode, int32_t n_threads,
+                               double eps_m, int64_t* boundary_counts) {
+  return process_batch_impl(P, points, scan_offsets, roll_pitch, n_scans, mode, n_threads, nullptr, nullptr, nullptr,
+                            nullptr, 0, nullptr, eps_m, boundary_counts);
+}
+
+// The host libm's float routines, element-wise: op 0 = atan2f(a, b), 1 = acosf(a), 2 = atanf(a).
+// What tests/ compare the device's restatement (csrc/glibc_f32.h) against.
+void feo_libm_f32(int32_t op, const float* a, const float* b, float* out, int64_t n) {
+  for (int64_t i = 0; i < n; i++) {
+    volatile float x = a[i];
+    out[i] = op == 0 ? atan2f(x, b[i]) : op == 1 ? acosf(x) : atanf(x);
+  }
 }
 
 }  // extern "C"

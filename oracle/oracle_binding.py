@@ -249,3 +249,26 @@ def process_batch(params, points, scan_offsets, roll_pitch, mode=1, n_threads=1,
         break
     k = tot.value
     return ko, kp[:k].copy(), (d[:k].copy() if d is not None else None), (m[:k].copy() if m is not None else None)
+
+
+def process_batch_boundary(params, points, scan_offsets, roll_pitch, eps_m=1e-6, mode=1, n_threads=1):
+    """Tolerance-boundary report of the oracle: (B, 4) int64 pair counts within eps_m of the radius of
+    [ring clustering, cross-ring merge, 3DSC support, 3DSC density] (see feo_process_batch_boundary)."""
+    c = _pts(points)
+    offs = np.ascontiguousarray(scan_offsets, np.int64)
+    rp = np.ascontiguousarray(roll_pitch, np.float64).reshape(-1)
+    B = len(offs) - 1
+    out = np.zeros((max(B, 1), 4), np.int64)
+    st = lib().feo_process_batch_boundary(C.byref(params), _p(c), _p(offs), _p(rp), C.c_int32(B), C.c_int32(mode),
+                                          C.c_int32(n_threads), C.c_double(eps_m), _p(out))
+    assert st == 0, st
+    return out[:B]
+
+
+def libm_f32(op, a, b=None):
+    """The host libm (glibc) element-wise: op 0 atan2f(a, b), 1 acosf(a), 2 atanf(a)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b if b is not None else a, np.float32)
+    out = np.empty_like(a)
+    lib().feo_libm_f32(C.c_int32(op), _p(a), _p(b), _p(out), C.c_int64(a.size))
+    return out

@@ -27,9 +27,9 @@ def test_empty_batch_and_empty_scans(ob, synth, node):
     offs2 = np.array([0, 0, offs[1], offs[1], offs[2], offs[3], offs[3]], np.int64)
     rp2 = np.array([[0, 0], rp[0], [0, 0], rp[1], rp[2], [0, 0]])
     ko, kp, d = node.processBatch(pts, offs2, rp2)
-    ko_o, kp_o, d_o, m = ob.process_batch(ob.node_default(), pts, offs2, rp2, mode=0, want_margin=True)
+    ko_o, kp_o, d_o, m = ob.process_batch(ob.node_default(), pts, offs2, rp2, mode=0)
     assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o)
-    assert check_descriptors(d, d_o, m)[2] == 0
+    assert check_descriptors(d, d_o)[1] == 0
     for fn in (node.getElevationAngles, node.rotateCloud, node.filterCloud):
         assert len(fn(e)) == 0
     assert node.extractClusters(e, 0.65, 1, 10) == []
@@ -50,7 +50,7 @@ def test_non_finite_points_and_out_of_crop(ob, synth, node):
     r = ob.process_scan(P, pts, rp[0, 0], rp[0, 1], mode=0)
     ko, kp, d = node.processBatch(pts, offs, rp)
     assert bits_equal(kp, r["keypoints"])
-    assert check_descriptors(d, r["descriptors"], r["edge_margin"])[2] == 0
+    assert check_descriptors(d, r["descriptors"])[1] == 0
     el_g = node.getElevationAngles(pts)
     el_o = ob.get_elevation_angles(pts)
     fin = np.isfinite(el_o[:, 3])
@@ -104,7 +104,7 @@ def test_zero_neighbour_keypoint_gives_nan_descriptor(ob, node):
     d_o, m, nn = ob.estimate_descriptors(P, cloud, kps)
     d_g = node.estimateDescriptors(cloud, kps)
     assert np.all(np.isnan(d_g[0])) and np.all(np.isnan(d_g[2]))
-    assert check_descriptors(d_g, d_o, m)[2] == 0
+    assert check_descriptors(d_g, d_o)[1] == 0
     # neighbour straight above the keypoint: NaN azimuth lands in bin l=0 on both sides
     cloud2 = np.array([[10, 0, 1.0, 0], [10.3, 0.1, 0.0, 0]], np.float32)
     kp2 = np.array([[10, 0, 0, 0]], np.float32)
@@ -158,7 +158,7 @@ def test_full_batch_size_properties(ob, synth):
     for s in sample:
         r = ob.process_scan(P, pts[offs[s]:offs[s + 1]], rp[s, 0], rp[s, 1], mode=1)
         assert bits_equal(kp_a[ko_a[s]:ko_a[s + 1]], r["keypoints"]), s
-        assert check_descriptors(d_a[ko_a[s]:ko_a[s + 1]], r["descriptors"], r["edge_margin"])[2] == 0
+        assert check_descriptors(d_a[ko_a[s]:ko_a[s + 1]], r["descriptors"])[1] == 0
     # a scan's result does not depend on its neighbours in the batch: reversed batch order
     sel = sample[::-1]
     p2 = np.concatenate([pts[offs[s]:offs[s + 1]] for s in sel])
@@ -235,14 +235,14 @@ def test_descriptors_off_and_parameter_changes_on_a_live_context(ob, synth):
     L = ob.launch_playback()
     nd.set_params(to_fe_params(L))
     ko, kp, d = nd.processBatch(pts, offs, rp)
-    ko_o, kp_o, d_o, m = ob.process_batch(L, pts, offs, rp, mode=1, n_threads=4, want_margin=True)
-    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o) and check_descriptors(d, d_o, m)[2] == 0
+    ko_o, kp_o, d_o, m = ob.process_batch(L, pts, offs, rp, mode=1, n_threads=4)
+    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o) and check_descriptors(d, d_o)[1] == 0
     P.estimate_descriptors = 1
     P.descriptor_radius = 1.5
     nd.set_params(to_fe_params(P))
     ko, kp, d = nd.processBatch(pts, offs, rp)
-    ko_o, kp_o, d_o, m = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=4, want_margin=True)
-    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o) and check_descriptors(d, d_o, m)[2] == 0
+    ko_o, kp_o, d_o, m = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=4)
+    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o) and check_descriptors(d, d_o)[1] == 0
     nd.close()
 
 
@@ -280,11 +280,11 @@ def test_random_parameter_sets_match_the_oracle(ob, synth):
         else:
             nd.set_params(to_fe_params(P))
         ko, kp, d = nd.processBatch(pts, offs, rp)
-        ko_o, kp_o, d_o, m = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=8, want_margin=True)
+        ko_o, kp_o, d_o, m = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=8)
         tag = (trial, P.cluster_tolerance, P.cluster_radius_threshold, P.descriptor_radius, int(ko_o[-1]))
         assert np.array_equal(ko, ko_o), tag
         assert bits_equal(kp, kp_o), tag
-        assert check_descriptors(d, d_o, m)[2] == 0, tag
+        assert check_descriptors(d, d_o)[1] == 0, tag
     nd.close()
 
 
@@ -302,5 +302,5 @@ def test_very_large_scan_takes_the_deferred_paths(ob, synth):
     r = ob.process_scan(P, pts, rp[0, 0], rp[0, 1], mode=1)
     assert len(r["cloud_full"]) == len(pts)
     assert bits_equal(kp, r["keypoints"])
-    assert check_descriptors(d, r["descriptors"], r["edge_margin"])[2] == 0
+    assert check_descriptors(d, r["descriptors"])[1] == 0
     nd.close()

@@ -2,7 +2,8 @@
 
 Bar (BASELINE.json north_star): cluster membership and keypoint sets bit-exact; keypoint
 coordinates and descriptor values within 1e-5 relative (they are bit-exact in practice, descriptor
-bins differ only by float summation order); tolerance-boundary cases reported separately.
+bins differ only by float summation order beyond 8192 neighbours); no whitelist of any kind.  The
+tolerance-boundary report the north star asks for is a separate count (test_boundary_report...).
 """
 import numpy as np
 import pytest
@@ -73,8 +74,8 @@ def test_each_reference_function_matches_the_oracle(ob, synth, nodes, cfg):
         # H-N estimateDescriptors (src:329-355)
         if len(kp_o):
             d_g = nd.estimateDescriptors(r["cloud_full"], kp_o)
-            ok, boundary, bad = check_descriptors(d_g, r["descriptors"], r["edge_margin"])
-            assert bad == 0, (ok, boundary, bad)
+            ok, bad = check_descriptors(d_g, r["descriptors"])
+            assert bad == 0, (ok, bad)
 
 
 @pytest.mark.parametrize("cfg,nscans", [(1, 6), (2, 48), (3, 3), (4, 4)])
@@ -87,12 +88,11 @@ def test_fused_batch_matches_the_oracle(ob, synth, nodes, cfg, nscans):
     ko, kp, d = nd.processBatch(pts, offs, rp)
     co, cloud, kco, kcloud = nd.cloudOutputs(nscans)
     nd.enableCloudOutputs(False)
-    ko_o, kp_o, d_o, m_o = ob.process_batch(P, pts, offs, rp, mode=0, n_threads=8, want_margin=True)
+    ko_o, kp_o, d_o, _ = ob.process_batch(P, pts, offs, rp, mode=0, n_threads=8)
     assert np.array_equal(ko, ko_o)
     assert bits_equal(kp, kp_o)
-    ok, boundary, bad = check_descriptors(d, d_o, m_o)
-    assert bad == 0, (ok, boundary, bad)
-    assert boundary <= max(1, len(kp) // 50)
+    ok, bad = check_descriptors(d, d_o)
+    assert bad == 0, (ok, bad)
     for s in range(nscans):
         r = ob.process_scan(P, pts[offs[s]:offs[s + 1]], rp[s, 0], rp[s, 1], mode=1)
         assert bits_equal(cloud[co[s]:co[s + 1]], r["cloud"])
@@ -177,7 +177,7 @@ def test_descriptors_are_bit_identical_when_summed_in_pcl_order(ob, synth, nodes
         dg = d[ko[s]:ko[s + 1]]
         assert bits_equal(kp[ko[s]:ko[s + 1]], r["keypoints"])
         for i in range(len(dg)):
-            if r["n_neighbors"][i] <= 8192 and r["edge_margin"][i] > 2e-6:
+            if r["n_neighbors"][i] <= 8192:
                 total += 1
                 exact += int(bits_equal(dg[i], r["descriptors"][i]))
     assert total > 0 and exact == total, (exact, total)

@@ -148,3 +148,24 @@ def test_elevation_precedes_rotation(ob):
     rot = ob.rotate_cloud(el, 0.3, -0.2)
     assert rot[0, 3] == el[0, 3]
     assert not np.allclose(rot[0, :3], el[0, :3])
+
+
+def test_boundary_report_is_the_same_from_both_search_back_ends(ob, synth):
+    """The north star's "within 1e-6 m of a tolerance boundary" report: brute force sees every pair, the
+    KD-tree prunes with a margin wider than the band, so both count the same pairs; a pair built to sit
+    4e-7 m inside the cluster tolerance is reported, one 1 mm inside is not."""
+    P = ob.node_default()
+    pts, offs, rp = synth.generate(2, 6, scan_index_base=8200)
+    for eps in (1e-6, 1e-4):
+        a = ob.process_batch_boundary(P, pts, offs, rp, eps, mode=0, n_threads=4)
+        b = ob.process_batch_boundary(P, pts, offs, rp, eps, mode=1, n_threads=4)
+        assert a.shape == (6, 4) and np.array_equal(a, b)
+    assert a.sum() > 0
+    P.cluster_min_count = 1
+    t = np.tan(np.deg2rad(-1.0))
+    for gap, expect in ((0.6499996, True), (0.6489996, False)):
+        xs = [2.0 + 0.01 * k for k in range(5)] + [2.04 + gap / np.sqrt(1 + t * t)]
+        sc = np.array([(x, 0.5, x * t, 0.0) for x in xs], np.float32)
+        for mode in (0, 1):
+            r = ob.process_batch_boundary(P, sc, np.array([0, len(sc)], np.int64), np.zeros((1, 2)), 1e-6, mode=mode)
+            assert (r[0, 0] >= 1) == expect, (gap, mode, r)

@@ -28,21 +28,17 @@ def rel_err(a, b):
     return np.where(np.isnan(e), np.inf, e)
 
 
-# Descriptor tolerance of BASELINE.json:north_star: 1e-5 relative.  A keypoint whose nearest
-# neighbour-to-bin-edge margin is below EDGE_MARGIN can legitimately move one contribution to the
-# adjacent bin (libm acosf/atan2f vs the device's correctly rounded versions); such keypoints are
-# reported separately, as the north star prescribes for tolerance-boundary cases.
+# Descriptor tolerance of BASELINE.json:north_star: 1e-5 relative.  No whitelist: the device evaluates
+# atan2f / acosf exactly like the host libm (csrc/glibc_f32.h), so a neighbour on a bin edge lands in the
+# same bin on both sides and every row must meet the bar.
 DESC_RTOL = 1e-5
-EDGE_MARGIN = 2e-6
 
 
-def check_descriptors(d_gpu, d_ref, edge_margin):
-    """-> (n_ok, n_boundary, n_bad)"""
+def check_descriptors(d_gpu, d_ref):
+    """-> (n_ok, n_bad): descriptor rows within / beyond 1e-5 relative of the oracle's."""
     assert d_gpu.shape == d_ref.shape
     if len(d_gpu) == 0:
-        return 0, 0, 0
+        return 0, 0
     e = rel_err(d_gpu, d_ref).max(axis=1)
     ok = e <= DESC_RTOL
-    boundary = (~ok) & (edge_margin < EDGE_MARGIN)
-    bad = (~ok) & ~boundary
-    return int(ok.sum()), int(boundary.sum()), int(bad.sum())
+    return int(ok.sum()), int((~ok).sum())
