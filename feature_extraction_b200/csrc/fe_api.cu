@@ -27,6 +27,7 @@ struct Slot {
   int capKf = 0, capKc = 0;
   // device
   float4 *d_pts = nullptr, *d_surf = nullptr, *d_crop = nullptr, *d_sorted = nullptr, *d_full = nullptr;
+  float4* d_ringPts = nullptr;  // K2: the crop survivors bucketed by ring (CSR like the input)
   unsigned *d_cropMeta = nullptr, *d_keyA = nullptr, *d_keyB = nullptr, *d_valA = nullptr, *d_valB = nullptr, *d_sortedKey = nullptr;
   int* d_rho = nullptr;
   long long* d_scan_off = nullptr;
@@ -85,6 +86,7 @@ struct fe_ctx {
   int axesCap = 0;
   bool cloudOutputs = false;
   bool stageTiming = false;   // serialise the stages and time each with CUDA events (fe_enable_stage_timing)
+  bool gridClustering = false;  // fe_debug_force_grid_clustering: K2 through the grid-based kernels only
   bool recordOutput = false;  // descriptors leave as FE_RECORD_FLOATS-float PointDescriptor records
   int angleLibm = 0;          // fe_set_angle_libm
   double bndEps = 0.0;        // fe_enable_boundary_report: > 0 = count the pairs within bndEps of every radius
@@ -233,7 +235,7 @@ template <class T>
 cudaError_t halloc(T** p, size_t n) { return cudaHostAlloc((void**)p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault); }
 
 void free_slot(Slot& s) {
-  void* dv[] = {s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
+  void* dv[] = {s.d_ringPts, s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
                 s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd};
@@ -271,7 +273,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(cudaEventCreate(&s.evT1));
   const size_t np = (size_t)s.capPts, ns = (size_t)s.capScans;
   if (ownPoints) CK(dalloc(&s.d_pts, np));
-  CK(dalloc(&s.d_surf, np)); CK(dalloc(&s.d_crop, np)); CK(dalloc(&s.d_sorted, np));
+  CK(dalloc(&s.d_surf, np)); CK(dalloc(&s.d_crop, np)); CK(dalloc(&s.d_sorted, np)); CK(dalloc(&s.d_ringPts, np));
   CK(dalloc(&s.d_cropMeta, np)); CK(dalloc(&s.d_keyA, np)); CK(dalloc(&s.d_keyB, np));
   CK(dalloc(&s.d_valA, np)); CK(dalloc(&s.d_valB, np)); CK(dalloc(&s.d_sortedKey, np));
   CK(dalloc(&s.d_rho, np));
@@ -396,6 +398,7 @@ const size_t kClusterSmemM = cluster_smem_bytes(ECAP_M, NTM);
 
 int set_kernel_attrs(fe_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  CK(cudaFuncSetAttribute(k_ring_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingRunsSm)));
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NTL, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL2));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
@@ -496,7 +499,14 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
   const int sr = singleRing ? 1 : 0;
 #define FE_K2_ARGS s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, \
                    s.capKc, kcB, kcC, s.d_ctr
-  k_cluster_rings<ECAP, NTF, 4, false><<<nscans, NTF, kClusterSmem, s.stream>>>(FE_K2_ARGS, nullptr, nullptr, s.d_ovfRings, ovfR, nullptr);
+  // K2: the run-based kernel takes every scan; what it cannot handle (a ring with more than RW runs — unordered
+  // input — or more ring entries than the scan's scratch slot) goes down the chain of grid-based instantiations.
+  if (ctx->gridClustering)
+    k_cluster_rings<ECAP, NTF, 4, false><<<nscans, NTF, kClusterSmem, s.stream>>>(FE_K2_ARGS, nullptr, nullptr, s.d_ovfRings, ovfR, nullptr);
+  else
+    k_ring_runs<<<nscans, NT_RR, sizeof(RingRunsSm), s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr,
+                                                                 s.d_ringPts, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC,
+                                                                 s.d_ctr, s.d_ovfRings, ovfR);
   k_cluster_rings<ECAP_L, NTL, 1, false><<<gridL, NTL, kClusterSmemL2, s.stream>>>(FE_K2_ARGS, s.d_ovfRings, ovfR, s.d_ovfRings2, ovfR2, nullptr);
   k_cluster_rings<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K2_ARGS, s.d_ovfRings2, ovfR2, nullptr, nullptr, s.d_slabs);
 #undef FE_K2_ARGS
@@ -1518,6 +1528,15 @@ int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_
   out->on_device = 0;
   out->gpu_launches = 0;
   for (int g = 0; g < G; g++) out->gpu_launches += res[g].gpu_launches;
+  return FE_OK;
+}
+
+// debug / test hook: run K2 through the grid-based kernels only (the general fallback of the run-based kernel), so
+// that tests can cross-check the two algorithms against each other and against the oracle
+int fe_debug_force_grid_clustering(fe_ctx_t* ctx, int32_t enable) {
+  if (!ctx) return FE_ERR_INVALID;
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+  ctx->gridClustering = enable != 0;
   return FE_OK;
 }
 

@@ -989,6 +989,10 @@ __global__ void __launch_bounds__(NT, MINB) k_cluster_rings(
   }
 }
 
+}  // namespace fe
+#include "fe_ring_runs.cuh"
+namespace fe {
+
 // ============================================================================================
 // K3 — cross-ring merge (src:205-257) for one scan per block; also the stage kernel behind
 // fe_extract_clusters when `stage` != 0 (then it just reports the clusters of `crop`).

@@ -312,6 +312,10 @@ class FeatureExtractionNode:
             return np.zeros((0, 4), np.int64)
         return np.ctypeslib.as_array(p, shape=(n.value, 4)).copy()
 
+    def forceGridClustering(self, enable=True):
+        """Test hook: K2 through the grid-based kernels only (the run-based kernel's fallback and cross-check)."""
+        self._check(N.lib().fe_debug_force_grid_clustering(self._ctx, 1 if enable else 0))
+
     def debugLibm(self, op, a, b=None):
         """Test hook: the device's atan2f (op 0), acosf (1), atanf (2) element-wise."""
         a = np.ascontiguousarray(a, np.float32)

@@ -267,3 +267,35 @@ def test_stage_timing_mode_serialises_without_changing_results(ob, synth, nodes)
     for want in ("K1 level+crop+ring", "K2 ring clusters", "K3 merge keypoints", "K4a surface grid", "K4b mark neighbours",
                  "K4c density", "K4d shape context"):
         assert want in names and want in names_dev
+
+
+@pytest.mark.parametrize("cfg,nscans", [(1, 6), (2, 64), (3, 4), (4, 6)])
+def test_run_based_and_grid_based_ring_clustering_agree(ob, synth, nodes, cfg, nscans):
+    """Row E2/F two ways: the run-based K2 (rings in firing order cut into runs, links between runs) and
+    the grid-based kernels it falls back to (cell grid + union-find) must give the oracle's keypoints and
+    keypoint_cloud bit for bit — also on rings whose entries arrive in arbitrary order, where every entry
+    is a run of its own and scans with more than 256 runs in a ring take the fallback."""
+    P = _params(ob, cfg)
+    nd = nodes(cfg)
+    pts, offs, rp = synth.generate(cfg, nscans, scan_index_base=7700)
+    ko_o, kp_o, _, _ = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=8, want_desc=False)
+    nd.enableCloudOutputs(True)
+    res = {}
+    for grid in (False, True):
+        nd.forceGridClustering(grid)
+        ko, kp, d = nd.processBatch(pts, offs, rp)
+        res[grid] = (ko, kp, d) + nd.cloudOutputs(nscans)
+    nd.forceGridClustering(False)
+    nd.enableCloudOutputs(False)
+    for grid in (False, True):
+        assert np.array_equal(res[grid][0], ko_o) and bits_equal(res[grid][1], kp_o), grid
+    assert np.array_equal(res[False][5], res[True][5]) and bits_equal(res[False][6], res[True][6])  # ~keypoint_cloud
+    # the same scans with every scan's points shuffled: same clusters, other order of discovery
+    rng = np.random.default_rng(3)
+    n2 = min(nscans, 3)
+    sh = pts[: offs[n2]].copy()
+    for s in range(n2):
+        sh[offs[s]:offs[s + 1]] = sh[offs[s]:offs[s + 1]][rng.permutation(int(offs[s + 1] - offs[s]))]
+    ko_o, kp_o, _, _ = ob.process_batch(P, sh, offs[: n2 + 1], rp[:n2], mode=1, n_threads=8, want_desc=False)
+    ko, kp, d = nd.processBatch(sh, offs[: n2 + 1], rp[:n2])
+    assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o)
