@@ -3,6 +3,11 @@
 
 A "step" is one pass of the hot path (reference cloudCallback, src:83-117) over one batch of
 synthetic VLP-16 scans: BASELINE.json configs[1] — 10k scans, node_default parameters — per GPU.
+The one JSON line also carries, under "configs", the same measurement for BASELINE.json's other
+configurations (1 single scan, 3 dense urban, 4 descriptor-heavy: value, e2e, roofline, 1-thread CPU
+baseline) and, under "config5", the 100k-scan sweep sharded over the N ranks (strong scaling, host-side
+gather inside the timed region, next to a bare pinned H2D copy probe).  `--config C` measures one
+configuration alone; `--no-subrecords` keeps the line to the main workload.
 
   value : whole-job scans/s with the points already resident in HBM (fe_process_batch_device),
           timed with CUDA events on the library's stream, max over ranks.
@@ -49,7 +54,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--config", type=int, default=0, help="1-5: that configuration alone; default: config 2 plus sub-records")
+    ap.add_argument("--no-subrecords", action="store_true")
+    ap.add_argument("--sweep-scans", type=int, default=100000, help="total scans of the config-5 sweep")
+    ap.add_argument("--in-process", action="store_true", help="config 5 through fe_multi_process_batch: ONE process, --gpus GPUs")
     ap.add_argument("--scans", type=int, default=0, help="scans per GPU per step (default: the config's batch)")
     ap.add_argument("--cpu-sample", type=int, default=1536, help="scans of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,7 +65,7 @@ def parse():
 
 
 def default_scans(cfg):
-    return {1: 1, 2: 10000, 3: 2500, 4: 1000}[cfg]
+    return {1: 1, 2: 10000, 3: 2500, 4: 1000, 5: 10000}[cfg]
 
 
 def oracle_params(ob, cfg):
@@ -65,6 +73,9 @@ def oracle_params(ob, cfg):
     if cfg == 4:
         P.descriptor_radius = 5.0
     return P
+
+
+CONFIG_DESC[5] = "config5: 100k-scan sweep of config-2 scans sharded over the GPUs (scan-parallel, host-side gather)"
 
 
 def product_params(cfg):
@@ -142,7 +153,7 @@ def run_reference(args, rank, world):
         return
     from feature_extraction_b200 import synth
     from oracle import oracle_binding as ob
-    cfg = args.config
+    cfg = args.config or 2
     P = oracle_params(ob, cfg)
     cores = host_threads()
     n = max(8, min(args.cpu_sample, args.scans or default_scans(cfg)))
@@ -168,8 +179,10 @@ def run_reference(args, rank, world):
     emit(out)
 
 
+
 def stage_bytes(st, desc_len=1980):
-    """Algorithmic (compulsory) bytes of every timed stage for one launch — DESIGN.md §Kernels."""
+    """Algorithmic (compulsory single-pass) bytes of every timed stage for one launch.  ONE table:
+    DESIGN.md §5 and BASELINE.md §4 quote these same expressions."""
     N, Ns, Nc, Kf, K, M = (st[k] for k in ("points", "surface_points", "crop_points", "ring_clusters", "keypoints", "neighbours"))
     return {
         "K1 level+crop+ring": 16 * N + 16 * Ns + 20 * Nc,
@@ -181,6 +194,392 @@ def stage_bytes(st, desc_len=1980):
         "K4c density": 20 * M,
         "K4d shape context": 20 * M + 4 * desc_len * K,
     }
+
+
+def survey_bytes(st):
+    """SURVEY.md §8d's byte accounting (a global-memory multi-pass design: K2a+K2b+K2c, K4a incl. density,
+    K4b incl. the histogram), reported as a second fraction beside the fused design's own bytes."""
+    N, Nc, Kf, K, M = (st[k] for k in ("points", "crop_points", "ring_clusters", "keypoints", "neighbours"))
+    return {
+        "K1": (("K1 level+crop+ring",), 32 * N + 20 * Nc),
+        "K2 (K2a+K2b+K2c)": (("K2 ring clusters",), 72 * Nc + 28 * Nc + 20 * Nc + 56 * Kf),
+        "K3": (("K3 merge keypoints", "keypoint CSR"), 16 * Kf + 16 * K),
+        "K4a (grid+density)": (("K4a surface grid", "K4c density"), 92 * N),
+        "K4b (gather+histogram)": (("K4b mark neighbours", "K4d shape context"), 20 * M + 7956 * K),
+    }
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class Job:
+    """rank / world plumbing shared by the measurements."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def descriptor_parity(dg, d_o):
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = np.abs(dg.astype(np.float64) - d_o) / np.maximum(np.abs(d_o), 1e-300)
+    rel = np.where((dg == d_o) | (np.isnan(dg) & np.isnan(d_o)), 0.0, rel)
+    rel = np.where(np.isnan(rel), np.inf, rel)
+    rows = rel.max(axis=1) if len(rel) else np.zeros(0)
+    return {"keypoints": int(len(dg)), "rows_bit_identical": int((dg.view(np.uint32) == d_o.view(np.uint32)).all(axis=1).sum()),
+            "rows_beyond_1e-5": int((rows > 1e-5).sum()), "max_rel_err": float(rows.max()) if len(rows) else 0.0}
+
+
+def measure(job, cfg, B, steps, warmup, cpu_sample=0, packed=False):
+    """One configuration on every rank (each its own B scans): device-resident value, per-stage times and
+    roofline, e2e through the host entry point, optional 1-thread CPU baseline (rank 0 of a 1-GPU job)."""
+    torch = job.torch
+    from feature_extraction_b200 import FeatureExtractionNode, PinnedBuffer, synth
+    A = synth.default_azimuth_steps(cfg)
+    pin = PinnedBuffer((16 * A * B, 4), np.float32)
+    pts, offs, rp = synth.generate(cfg, B, scan_index_base=job.rank * B, out=pin.array)
+    npts = int(offs[-1])
+    P = product_params(cfg)
+    est_kp = max(4096, B * (64 if cfg in (3, 4) else 16))
+    dev_node = FeatureExtractionNode(P, device=job.local_rank, max_points=npts + 4096, max_scans=B, max_keypoints=est_kp,
+                                     max_ring_clusters=max(1 << 20, B * 512))
+    d_pts = torch.empty((max(npts, 1), 4), dtype=torch.float32, device="cuda")
+    d_pts[:npts].copy_(torch.from_numpy(pts), non_blocking=False)
+    torch.cuda.synchronize()
+
+    # ---- value: device-resident hot path ----
+    for _ in range(warmup):
+        dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
+    job.barrier()
+    launches = 0
+    dev_node.timerBegin()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ko, K, p_kp, p_d = dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
+        launches += dev_node.last_launches
+    ev_ms = dev_node.timerEnd()
+    job.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_step = job.max_over_ranks(ev_ms / steps)
+    value = job.world * B / (ms_step * 1e-3)
+    stats = dev_node.batchStats()
+    # Per-kernel durations for the roofline: the same steps repeated right here with the stages serialised
+    # (fe_enable_stage_timing) and every stage bracketed by CUDA events on the launching stream.
+    stage_acc = {}
+    dev_node.enableStageTiming(True)
+    dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
+    dev_node.timerBegin()
+    for _ in range(steps):
+        dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
+        for nm, ms in dev_node.stageTimes():
+            stage_acc[nm] = stage_acc.get(nm, 0.0) + ms
+    serial_ms_step = dev_node.timerEnd() / steps
+    dev_node.enableStageTiming(False)
+    stage_ms = {k: v / steps for k, v in stage_acc.items()}
+
+    # ---- roofline ----
+    peak, peak_src = hbm_peak()
+    sb = stage_bytes(stats)
+    kernels = {}
+    for nm, ms in stage_ms.items():
+        gbs = sb.get(nm, 0) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        kernels[nm] = {"ms": ms, "algorithmic_bytes": sb.get(nm, 0), "gbs": gbs, "frac": gbs / peak}
+    dom = max((k for k in stage_ms if k in sb), key=stage_ms.get) if stage_ms else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if dom and cfg == 2 and os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(dom)
+        if rec and rec.get("scans"):
+            traffic = rec["dram_bytes_per_launch"] * (B / rec["scans"])
+    roofline = None
+    if dom:
+        tot_ms = max(sum(stage_ms.values()), 1e-9)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "share_of_step": stage_ms[dom] / tot_ms}
+        streaming = [k for k in ("K1 level+crop+ring", "K4a surface grid") if k in kernels]
+        if streaming:
+            best = max(streaming, key=lambda k: stage_ms[k])
+            roofline["largest_hbm_streaming_kernel"] = {"kernel": best, "achieved": kernels[best]["gbs"], "frac": kernels[best]["frac"],
+                                                        "share_of_step": stage_ms[best] / tot_ms}
+        # the second accounting (SURVEY.md §8d bytes) and the whole pipeline's compulsory I/O over the step time
+        sv = {}
+        for nm, (stages, nbytes) in survey_bytes(stats).items():
+            ms = sum(stage_ms.get(x, 0.0) for x in stages)
+            if ms > 0:
+                sv[nm] = {"ms": ms, "bytes": nbytes, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+        roofline["survey_8d_accounting"] = sv
+        io = 16 * stats["points"] + (16 + 7956) * stats["keypoints"]
+        roofline["whole_pipeline"] = {"compulsory_io_bytes": io, "frac": io / (ms_step * 1e-3) / 1e9 / peak}
+
+    # ---- e2e: host buffers through fe_process_batch (H2D + kernels + D2H inside the timed region) ----
+    dev_node.close()
+    del d_pts
+    torch.cuda.empty_cache()
+    sub_scans = max(64, min(1024, B))
+    sub_pts = int(min(npts + 4096, (npts / max(B, 1)) * sub_scans * 1.5 + 16 * A * 4))
+    host_node = FeatureExtractionNode(P, device=job.local_rank, max_points=sub_pts, max_scans=sub_scans,
+                                      max_keypoints=max(4096, sub_scans * (64 if cfg in (3, 4) else 16)))
+    for _ in range(warmup):
+        ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)
+    job.barrier()
+    t0 = time.perf_counter()
+    e2e_launches = 0
+    for _ in range(steps):
+        ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)
+        e2e_launches += host_node.last_launches
+    torch.cuda.synchronize()
+    e2e_ms = job.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    if job.world > 1:
+        job.dist.barrier()
+    e2e_value = job.world * B / (e2e_ms * 1e-3)
+    h2d = npts * 16 + (B + 1) * 12 + B * 36
+    d2h = int(len(kp)) * 16 + (0 if d is None else int(len(kp)) * 1980 * 4) + (B + 1) * 4 + 32
+    out = {
+        "value": value, "unit": "scans/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+        "config": {"workload": CONFIG_DESC[cfg], "scans_per_gpu": B, "points_per_scan_mean": npts / max(B, 1), "input_bytes_per_gpu": npts * 16,
+                   "l2": "inputs larger than L2, no flush needed" if npts * 16 > 256e6 else "inputs smaller than L2 (single-scan latency case)",
+                   "parallelism": "scan-parallel x%d, no collective" % job.world},
+        "mpoints_per_s": value * npts / max(B, 1) / 1e6,
+        "wall_ms_per_step": wall_ms / steps,
+        "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "mpoints_per_s": e2e_value * npts / max(B, 1) / 1e6, "sub_batch_scans": sub_scans},
+        "gpu_launches": launches, "gpu_launches_e2e": e2e_launches,
+        "roofline": roofline, "kernels": kernels, "serial_ms_per_step": serial_ms_step, "work": stats,
+    }
+    if packed:
+        # the same call with packed 12-byte xyz records (the path never reads the input intensity, src:154)
+        pin12 = PinnedBuffer((max(npts, 1), 3), np.float32)
+        pin12.array[:npts] = pts[:, :3]
+        for _ in range(2):
+            host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
+        job.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ko12, kp12, d12 = host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
+        torch.cuda.synchronize()
+        e2e12_ms = job.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+        same12 = bool(np.array_equal(ko12, ko) and np.array_equal(kp12.view(np.uint32), kp.view(np.uint32)))
+        ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)  # leave the float4 results in place for the checks below
+        pin12.free()
+        out["e2e_packed_xyz"] = {"value": job.world * B / (e2e12_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e12_ms,
+                                 "h2d_bytes_per_step": npts * 12 + (B + 1) * 12 + B * 36, "same_keypoints_as_float4": same12,
+                                 "note": "fe_process_batch_layout with 12-byte xyz records"}
+        probe_ms = job.max_over_ranks(min(host_node.h2dProbe(pts) for _ in range(3)))
+        out["h2d_probe"] = {"gbs": job.world * npts * 16 / (probe_ms * 1e-3) / 1e9, "ms": probe_ms,
+                            "e2e_over_probe": (npts * 16 / (e2e_ms * 1e-3)) / (npts * 16 / (probe_ms * 1e-3)),
+                            "note": "bare cudaMemcpyAsync of the same pinned points, all ranks at once, max over ranks"}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only); doubles as an in-run parity check ----
+    if cpu_sample > 0 and job.rank == 0 and job.world == 1:
+        from oracle import oracle_binding as ob
+        OP = oracle_params(ob, cfg)
+        n = max(1, min(cpu_sample, B))
+        o2 = offs[: n + 1]
+        reps = max(1, cpu_sample // n) if n < cpu_sample else 1  # a single scan is repeated so that the clock sees >= cpu_sample scans
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ko_o, kp_o, d_o, _ = ob.process_batch(OP, pts, o2, rp[:n], mode=1, n_threads=1)
+        dt1 = (time.perf_counter() - t0) / reps
+        cores = host_threads()
+        t0 = time.perf_counter()
+        ob.process_batch(OP, pts, o2, rp[:n], mode=1, n_threads=cores, want_desc=False if cfg == 3 else True)
+        dtn = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / dt1, "unit": "scans/s", "cores": 1, "kind": "port",
+                               "sample": "first %d scans of the workload, KD-tree oracle, 1 thread (how the reference runs: ros::spin)" % n}
+        if cfg != 3:
+            out["cpu_baseline"]["all_cores"] = {"value": n / dtn, "cores": cores}
+        same = bool(np.array_equal(ko[: n + 1], ko_o) and np.array_equal(kp[: ko[n]].view(np.uint32), kp_o.view(np.uint32)))
+        out["parity_vs_oracle_on_sample"] = same
+        if same and d is not None and d_o is not None:
+            out["descriptor_parity_on_sample"] = descriptor_parity(d[: ko[n]], d_o)
+    host_node.close()
+    pin.free()
+    torch.cuda.empty_cache()
+    return out
+
+
+def host_mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
+def measure_sweep(job, total, steps, warmup):
+    """BASELINE.json configs[4]: one sweep of `total` config-2 scans split into contiguous shards, one per
+    rank (strong scaling).  value: every rank's shard resident in HBM, processed in 10k-scan sub-batches;
+    e2e: pinned host shard through fe_process_batch, then the host-side gather of all ranks' results in scan
+    order on rank 0 (feature_extraction_b200.sharding.SharedGather) — all inside the timed region."""
+    torch = job.torch
+    from feature_extraction_b200 import FeatureExtractionNode, PinnedBuffer, synth
+    from feature_extraction_b200.sharding import SharedGather, shard_range
+    A = synth.default_azimuth_steps(2)
+    # bounded by host memory: the whole sweep sits in pinned memory on this box (16 B x ~14k points per scan)
+    per_scan = int(16 * A * 0.56)  # mean returns per scan are ~0.485 of the 16 x A rays (dropped no-return rays); 15 % headroom
+    avail = host_mem_available_bytes()
+    need = total * per_scan * 28  # float4 + packed xyz copies, both pinned
+    if avail and need > 0.35 * avail:
+        total = int(total * 0.35 * avail / need)
+    lo, hi = shard_range(total, job.rank, job.world)
+    B = hi - lo
+    pin = PinnedBuffer((per_scan * max(B, 1) + 16 * A, 4), np.float32)
+    t0 = time.perf_counter()
+    pts, offs, rp = synth.generate(2, B, scan_index_base=1_000_000 + lo, out=pin.array,
+                                   n_threads=max(1, host_threads() // max(job.world, 1)))
+    gen_s = time.perf_counter() - t0
+    npts = int(offs[-1])
+    P = product_params(2)
+    sub = 10000
+    sub_max_pts = int(max(offs[min(i + sub, B)] - offs[i] for i in range(0, max(B, 1), sub))) if B else 0
+    dev_node = FeatureExtractionNode(P, device=job.local_rank, max_points=sub_max_pts + 4096, max_scans=sub, max_keypoints=max(4096, sub * 16),
+                                     max_ring_clusters=max(1 << 20, sub * 512))
+    d_pts = torch.empty((max(npts, 1), 4), dtype=torch.float32, device="cuda")
+    d_pts[:npts].copy_(torch.from_numpy(pts), non_blocking=False)
+    torch.cuda.synchronize()
+
+    def device_pass():
+        n = 0
+        for i in range(0, B, sub):
+            j = min(i + sub, B)
+            dev_node.processBatchDevice(d_pts.data_ptr(), offs[i:j + 1], rp[i:j])
+            n += dev_node.last_launches
+        return n
+    for _ in range(warmup):
+        device_pass()
+    job.barrier()
+    dev_node.timerBegin()
+    launches = 0
+    for _ in range(steps):
+        launches += device_pass()
+    ev_ms = dev_node.timerEnd()
+    job.barrier()
+    ms_step = job.max_over_ranks(ev_ms / steps)
+    dev_node.close()
+    del d_pts
+    torch.cuda.empty_cache()
+
+    sub_scans = 1024
+    sub_pts = int(min(npts + 4096, (npts / max(B, 1)) * sub_scans * 1.5 + 16 * A * 4))
+    host_node = FeatureExtractionNode(P, device=job.local_rank, max_points=sub_pts, max_scans=sub_scans, max_keypoints=max(4096, sub_scans * 16))
+    sg = SharedGather()
+    res = None
+    for _ in range(warmup):
+        ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)
+        res = sg.gather(ko, kp, d)
+    job.barrier()
+    t0 = time.perf_counter()
+    t_gather = 0.0
+    for _ in range(steps):
+        ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)
+        tg = time.perf_counter()
+        res = sg.gather(ko, kp, d)
+        t_gather += time.perf_counter() - tg
+    torch.cuda.synchronize()
+    e2e_ms = job.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    gather_ms = job.max_over_ranks(t_gather * 1e3 / steps)
+    K_total = int(res[0][-1]) if (job.rank == 0 and res is not None) else 0
+    ordered = bool(job.rank != 0 or (len(res[0]) == total + 1 and np.all(np.diff(res[0]) >= 0)))
+    # the same with packed 12-byte xyz records
+    pin12 = PinnedBuffer((max(npts, 1), 3), np.float32)
+    pin12.array[:npts] = pts[:, :3]
+    host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
+    job.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ko, kp, d = host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
+        sg.gather(ko, kp, d)
+    torch.cuda.synchronize()
+    e2e12_ms = job.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    pin12.free()
+    # fabric ceiling: bare pinned H2D copies of every rank's shard at the same time
+    job.barrier()
+    probe_ms = job.max_over_ranks(min(host_node.h2dProbe(pts) for _ in range(2)))
+    tot_pts = job.sum_over_ranks(float(npts))
+    sg.close()
+    host_node.close()
+    pin.free()
+    torch.cuda.empty_cache()
+    probe_gbs = tot_pts * 16 / (probe_ms * 1e-3) / 1e9
+    e2e_gbs = tot_pts * 16 / (e2e_ms * 1e-3) / 1e9
+    return {
+        "workload": CONFIG_DESC[5], "scaling": "strong", "total_scans": total, "scans_per_rank": B, "n_gpus": job.world,
+        "steps": steps, "warmup": warmup, "generation_s": gen_s,
+        "value": total / (ms_step * 1e-3), "unit": "scans/s", "ms_per_step": ms_step, "mpoints_per_s": tot_pts / (ms_step * 1e-3) / 1e6,
+        "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e_ms, "host_gather_ms_per_step": gather_ms,
+                "h2d_bytes_per_step": int(tot_pts * 16), "keypoints_gathered": K_total, "gathered_in_scan_order": ordered,
+                "input_gbs": e2e_gbs, "note": "fe_process_batch on every rank's shard + SharedGather of all results on rank 0, timed together"},
+        "e2e_packed_xyz": {"value": total / (e2e12_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e12_ms, "h2d_bytes_per_step": int(tot_pts * 12)},
+        "h2d_probe": {"gbs": probe_gbs, "ms": probe_ms, "e2e_over_probe": e2e_gbs / probe_gbs,
+                      "note": "bare cudaMemcpyAsync of the same pinned shards, all ranks at once, max over ranks"},
+        "gpu_launches": launches,
+    }
+
+
+def measure_sweep_in_process(args):
+    """config 5 through fe_multi_process_batch: ONE process, a host thread and a context per GPU, results
+    concatenated on the host in scan order by the library (inside the timed call)."""
+    from feature_extraction_b200 import MultiGpuExtractor, PinnedBuffer, synth
+    A = synth.default_azimuth_steps(2)
+    total = args.sweep_scans
+    per_scan = int(16 * A * 0.56)
+    avail = host_mem_available_bytes()
+    need = total * per_scan * 16
+    if avail and need > 0.35 * avail:
+        total = int(total * 0.35 * avail / need)
+    pin = PinnedBuffer((per_scan * total + 16 * A, 4), np.float32)
+    pts, offs, rp = synth.generate(2, total, scan_index_base=1_000_000, out=pin.array)
+    npts = int(offs[-1])
+    P = product_params(2)
+    G = args.gpus
+    sub_scans = 1024
+    sub_pts = int((npts / total) * sub_scans * 1.5 + 16 * A * 4)
+    m = MultiGpuExtractor(list(range(G)), P, max_points=sub_pts, max_scans=sub_scans, max_keypoints=max(4096, sub_scans * 16))
+    for _ in range(max(args.warmup, 1)):
+        ko, kp, d = m.processBatch(pts, offs, rp, copy=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ko, kp, d = m.processBatch(pts, offs, rp, copy=False)
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    m.close()
+    pin.free()
+    return {"workload": CONFIG_DESC[5], "form": "fe_multi_process_batch, one process", "scaling": "strong", "total_scans": total, "n_gpus": G,
+            "steps": args.steps, "warmup": args.warmup, "e2e": {"value": total / (ms * 1e-3), "unit": "scans/s", "ms_per_step": ms,
+                                                                 "h2d_bytes_per_step": npts * 16, "keypoints_gathered": int(ko[-1]),
+                                                                 "gathered_in_scan_order": bool(np.all(np.diff(ko) >= 0))}}
 
 
 _RESULT_FD = None
@@ -208,220 +607,72 @@ def emit(out):
 def main():
     args = parse()
     quiet_stdout()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    if args.in_process:
+        emit({"metric": "scans/sec", "impl": "ours", "config5_in_process": measure_sweep_in_process(args)})
         return
 
-    import torch
-    import torch.distributed as dist
-    from feature_extraction_b200 import FeatureExtractionNode, PinnedBuffer, synth
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    cfg = args.config
-    B = args.scans or default_scans(cfg)
-    A = synth.default_azimuth_steps(cfg)
-
-    # ---- synthetic input, straight into pinned host memory (each rank its own scans) ----
-    cap = 16 * A * B
-    pin = PinnedBuffer((cap, 4), np.float32)
-    pts, offs, rp = synth.generate(cfg, B, scan_index_base=rank * B, out=pin.array)
-    npts = int(offs[-1])
-
-    P = product_params(cfg)
-    est_kp = max(4096, B * (64 if cfg in (3, 4) else 16))
-    dev_node = FeatureExtractionNode(P, device=local_rank, max_points=npts + 4096, max_scans=B, max_keypoints=est_kp,
-                                     max_ring_clusters=max(1 << 20, B * 512))
-    d_pts = torch.empty((max(npts, 1), 4), dtype=torch.float32, device="cuda")
-    d_pts[:npts].copy_(torch.from_numpy(pts), non_blocking=False)
-    torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- value: device-resident hot path ----
-    # clocks / throttle reasons are sampled from before the warm-up to the end of the e2e phase (the
-    # device-resident timed region alone is shorter than one nvidia-smi sampling period)
+    job = Job(args)
+    cfg = args.config or 2
+    # clocks / throttle reasons are sampled over the whole run (the device-resident timed region alone is
+    # shorter than one nvidia-smi sampling period)
     phys = [g.strip() for g in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if g.strip()]
-    job_gpus = [phys[i] if i < len(phys) else i for i in range(world)]  # nvidia-smi wants physical indices / UUIDs
-    sampler = ClockSampler(job_gpus if rank == 0 else None)
+    job_gpus = [phys[i] if i < len(phys) else i for i in range(job.world)]  # nvidia-smi wants physical indices / UUIDs
+    sampler = ClockSampler(job_gpus if job.rank == 0 else None)
     sampler.start()
-    for _ in range(args.warmup):
-        dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
-    barrier()
-    launches = 0
-    dev_node.timerBegin()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ko, K, p_kp, p_d = dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
-        launches += dev_node.last_launches
-    ev_ms = dev_node.timerEnd()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    ms_step = max_over_ranks(ev_ms / args.steps)
-    value = world * B / (ms_step * 1e-3)
-    stats = dev_node.batchStats()
-    # Per-kernel durations for the roofline: the timed pipeline above runs K4a on a side stream next to
-    # K2/K3, so an event pair there would time two kernels at once.  The same steps are repeated right
-    # here with the stages serialised (fe_enable_stage_timing) and every stage bracketed by CUDA events
-    # on the launching stream; `serial_ms_per_step` is the step time of that mode.
-    stage_acc = {}
-    dev_node.enableStageTiming(True)
-    dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
-    dev_node.timerBegin()
-    for _ in range(args.steps):
-        dev_node.processBatchDevice(d_pts.data_ptr(), offs, rp)
-        for nm, ms in dev_node.stageTimes():
-            stage_acc[nm] = stage_acc.get(nm, 0.0) + ms
-    serial_ms_step = dev_node.timerEnd() / args.steps
-    dev_node.enableStageTiming(False)
-    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
 
-    # ---- roofline of the dominant kernel ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    sb = stage_bytes(stats)
-    kernels = {}
-    for nm, ms in stage_ms.items():
-        gbs = sb.get(nm, 0) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        kernels[nm] = {"ms": ms, "algorithmic_bytes": sb.get(nm, 0), "gbs": gbs, "frac": gbs / peak}
-    dom = max(stage_ms, key=stage_ms.get) if stage_ms else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if dom and os.path.exists(tpath):
-        rec = json.load(open(tpath)).get(dom)
-        if rec and rec.get("scans"):
-            traffic = rec["dram_bytes_per_launch"] * (B / rec["scans"])
-    roofline = None
-    if dom:
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                    "share_of_step": stage_ms[dom] / max(sum(stage_ms.values()), 1e-9)}
-        # K2/K3/K4c/K4d keep a scan (or a keypoint) in shared memory: their time is issue / shared-memory
-        # bound and their DRAM traffic equals their (small) algorithmic bytes, so an HBM fraction says
-        # little about them.  The kernels that do stream HBM are reported beside the dominant one.
-        streaming = [k for k in ("K1 level+crop+ring", "K4a surface grid") if k in kernels]
-        if streaming:
-            best = max(streaming, key=lambda k: stage_ms[k])
-            roofline["largest_hbm_streaming_kernel"] = {"kernel": best, "achieved": kernels[best]["gbs"], "frac": kernels[best]["frac"],
-                                                        "share_of_step": stage_ms[best] / max(sum(stage_ms.values()), 1e-9)}
+    if cfg == 5:
+        sw = measure_sweep(job, args.sweep_scans, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+        clocks = sampler.stop()
+        if job.rank == 0:
+            out = {"metric": "scans/sec", "value": sw["value"], "unit": "scans/s", "n_gpus": job.world, "steps": sw["steps"], "warmup": sw["warmup"],
+                   "ms_per_step": sw["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                   "data": "synthetic", "config": {"workload": sw["workload"], "total_scans": sw["total_scans"], "scans_per_gpu": sw["scans_per_rank"],
+                                                   "parallelism": "scan-parallel x%d, host-side gather, no collective" % job.world},
+                   "e2e": sw["e2e"], "e2e_packed_xyz": sw["e2e_packed_xyz"], "h2d_probe": sw["h2d_probe"], "gpu_launches": sw["gpu_launches"],
+                   "clocks": clocks}
+            emit(out)
+        if job.world > 1:
+            job.dist.destroy_process_group()
+        return
 
-    # ---- e2e: host buffers through fe_process_batch (H2D + kernels + D2H inside the timed region) ----
-    dev_node.close()
-    del d_pts
-    torch.cuda.empty_cache()
-    sub_scans = max(64, min(1024, B))
-    sub_pts = int(min(npts + 4096, (npts / max(B, 1)) * sub_scans * 1.5 + 16 * A * 4))
-    host_node = FeatureExtractionNode(P, device=local_rank, max_points=sub_pts, max_scans=sub_scans,
-                                      max_keypoints=max(4096, sub_scans * (64 if cfg in (3, 4) else 16)))
-    for _ in range(args.warmup):
-        ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_launches = 0
-    for _ in range(args.steps):
-        ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)
-        e2e_launches += host_node.last_launches
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
-    if world > 1:
-        dist.barrier()
-    e2e_value = world * B / (e2e_ms * 1e-3)
-    # the same call with packed 12-byte xyz records (the path never reads the input intensity, src:154)
-    pin12 = PinnedBuffer((max(npts, 1), 3), np.float32)
-    pin12.array[:npts] = pts[:, :3]
-    for _ in range(2):
-        host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ko12, kp12, d12 = host_node.processBatchLayout(pin12.array[:npts], 12, 0, 4, 8, offs, rp, copy=False)
-    torch.cuda.synchronize()
-    e2e12_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
-    same12 = bool(np.array_equal(ko12, ko) and np.array_equal(kp12.view(np.uint32), kp.view(np.uint32)))
-    ko, kp, d = host_node.processBatch(pts, offs, rp, copy=False)  # leave the float4 results in place for the checks below
-    pin12.free()
-    clocks = sampler.stop()
-    h2d = npts * 16 + (B + 1) * 12 + B * 36
-    d2h = int(len(kp)) * 16 + (0 if d is None else int(len(kp)) * 1980 * 4) + (B + 1) * 4 + 32
+    B = args.scans or default_scans(cfg)
+    want_cpu = 0 if args.no_cpu_baseline else args.cpu_sample
+    m = measure(job, cfg, B, args.steps, args.warmup, cpu_sample=want_cpu, packed=True)
+    clocks = sampler.stop() if (args.config or args.no_subrecords) else None
+    out = {"metric": "scans/sec", "value": m["value"], "unit": "scans/s", "n_gpus": job.world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    for k in ("config", "mpoints_per_s", "wall_ms_per_step", "e2e", "e2e_packed_xyz", "h2d_probe", "gpu_launches", "gpu_launches_e2e", "roofline",
+              "kernels", "serial_ms_per_step", "work", "cpu_baseline", "parity_vs_oracle_on_sample", "descriptor_parity_on_sample"):
+        if k in m:
+            out[k] = m[k]
+    out["kernels_note"] = ("per-stage CUDA-event times of %d extra steps run right after the timed region with the stages serialised "
+                           "(fe_enable_stage_timing; %.3f ms per step in that mode)" % (args.steps, m["serial_ms_per_step"]))
 
-    out = {
-        "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": CONFIG_DESC[cfg], "scans_per_gpu": B, "points_per_scan_mean": npts / max(B, 1),
-                   "input_bytes_per_gpu": npts * 16, "l2": "inputs larger than L2, no flush needed" if npts * 16 > 256e6 else "inputs smaller than L2",
-                   "parallelism": "scan-parallel x%d, no collective" % world},
-        "mpoints_per_s": value * npts / max(B, 1) / 1e6,
-        "wall_ms_per_step": wall_ms / args.steps,
-        "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "mpoints_per_s": e2e_value * npts / max(B, 1) / 1e6, "sub_batch_scans": sub_scans},
-        "e2e_packed_xyz": {"value": world * B / (e2e12_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e12_ms,
-                           "h2d_bytes_per_step": npts * 12 + (B + 1) * 12 + B * 36, "same_keypoints_as_float4": same12,
-                           "note": "fe_process_batch_layout with 12-byte xyz records"},
-        "gpu_launches": launches,
-        "gpu_launches_e2e": e2e_launches,
-        "clocks": clocks,
-        "roofline": roofline,
-        "kernels": kernels,
-        "kernels_note": "per-stage CUDA-event times of %d extra steps run right after the timed region with the stages serialised "
-                        "(fe_enable_stage_timing; %.3f ms per step in that mode); the timed pipeline overlaps K4a with K2/K3 on two streams" % (args.steps, serial_ms_step),
-        "serial_ms_per_step": serial_ms_step,
-        "work": stats,
-    }
-
-    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle_binding as ob
-        OP = oracle_params(ob, cfg)
-        n = max(1, min(args.cpu_sample, B))
-        o2 = offs[: n + 1]
-        t0 = time.perf_counter()
-        ko_o, kp_o, d_o, _ = ob.process_batch(OP, pts, o2, rp[:n], mode=1, n_threads=1)
-        dt1 = time.perf_counter() - t0
-        cores = host_threads()
-        t0 = time.perf_counter()
-        ob.process_batch(OP, pts, o2, rp[:n], mode=1, n_threads=cores)
-        dtn = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": n / dt1, "unit": "scans/s", "cores": 1, "kind": "port",
-                               "sample": "first %d scans of the workload, KD-tree oracle, 1 thread (how the reference runs: ros::spin)" % n,
-                               "all_cores": {"value": n / dtn, "cores": cores}}
-        # the sample doubles as an in-bench parity check of the timed path
-        same = bool(np.array_equal(ko[: n + 1], ko_o) and np.array_equal(kp[: ko[n]].view(np.uint32), kp_o.view(np.uint32)))
-        out["parity_vs_oracle_on_sample"] = same
-        if same and d is not None and d_o is not None:
-            dg = d[: ko[n]]
-            with np.errstate(invalid="ignore", divide="ignore"):
-                rel = np.abs(dg.astype(np.float64) - d_o) / np.maximum(np.abs(d_o), 1e-300)
-            rel = np.where((dg == d_o) | (np.isnan(dg) & np.isnan(d_o)), 0.0, rel)
-            rel = np.where(np.isnan(rel), np.inf, rel)
-            rows = rel.max(axis=1) if len(rel) else np.zeros(0)
-            out["descriptor_parity_on_sample"] = {
-                "keypoints": int(len(dg)), "rows_bit_identical": int((dg.view(np.uint32) == d_o.view(np.uint32)).all(axis=1).sum()),
-                "rows_beyond_1e-5": int((rows > 1e-5).sum()), "max_rel_err": float(rows.max()) if len(rows) else 0.0}
-    if rank == 0:
+    # ---- the other BASELINE.json configurations, in the same run (sub-records) ----
+    if not args.config and not args.no_subrecords:
+        subs = {}
+        for c, st, wu, cs in ((1, 200, 20, 96), (3, 5, 3, 96), (4, 5, 3, 96)):
+            try:
+                r = measure(job, c, default_scans(c), min(st, max(args.steps, 1) * 10), wu, cpu_sample=(0 if args.no_cpu_baseline else cs))
+                for k in ("kernels",):  # keep the line readable: stage times only
+                    r[k] = {nm: {"ms": v["ms"], "frac": v["frac"]} for nm, v in r[k].items()}
+                subs[str(c)] = r
+            except Exception as e:  # a sub-record must never cost the main line
+                subs[str(c)] = {"error": repr(e)[:300]}
+        out["configs"] = subs
+        try:
+            out["config5"] = measure_sweep(job, args.sweep_scans, 2, 1)
+        except Exception as e:
+            out["config5"] = {"error": repr(e)[:300]}
+        clocks = sampler.stop()
+    out["clocks"] = clocks
+    if job.rank == 0:
         emit(out)
-    host_node.close()
-    pin.free()
-    if world > 1:
-        dist.destroy_process_group()
+    if job.world > 1:
+        job.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -134,6 +134,7 @@ def lib():
         L.fe_set_angle_libm.argtypes = [C.c_void_p, C.c_int32]
         L.fe_enable_boundary_report.argtypes = [C.c_void_p, C.c_double]
         L.fe_get_boundary_report.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int32)]
+        L.fe_debug_h2d_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float)]
         L.fe_debug_force_grid_clustering.argtypes = [C.c_void_p, C.c_int32]
         L.fe_debug_libm_f32.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         _LIB = L

@@ -1531,6 +1531,25 @@ int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_
   return FE_OK;
 }
 
+// bench hook: bare pinned-host -> device copies of `bytes` from `host` into the context's staging buffer, chunk after
+// chunk on one stream, timed with CUDA events — the ceiling the host entry points can reach on this box
+int fe_debug_h2d_probe(fe_ctx_t* ctx, const void* host, int64_t bytes, float* ms) {
+  if (!ctx || !host || bytes < 0 || !ms) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[0];
+  int st = ensure_slot(ctx, s, true);
+  if (st) return st;
+  const int64_t chunk = s.capPts * (int64_t)sizeof(float4);
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaEventRecord(s.evT0, s.stream));
+  for (int64_t off = 0; off < bytes; off += chunk)
+    CK(cudaMemcpyAsync(s.d_pts, (const char*)host + off, (size_t)std::min(chunk, bytes - off), cudaMemcpyHostToDevice, s.stream));
+  CK(cudaEventRecord(s.evT1, s.stream));
+  CK(cudaEventSynchronize(s.evT1));
+  CK(cudaEventElapsedTime(ms, s.evT0, s.evT1));
+  return FE_OK;
+}
+
 // debug / test hook: run K2 through the grid-based kernels only (the general fallback of the run-based kernel), so
 // that tests can cross-check the two algorithms against each other and against the oracle
 int fe_debug_force_grid_clustering(fe_ctx_t* ctx, int32_t enable) {

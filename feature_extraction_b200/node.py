@@ -312,6 +312,12 @@ class FeatureExtractionNode:
             return np.zeros((0, 4), np.int64)
         return np.ctypeslib.as_array(p, shape=(n.value, 4)).copy()
 
+    def h2dProbe(self, host_array):
+        """Bench hook: bare host->device copy of `host_array` through the staging buffer; -> ms (CUDA events)."""
+        ms = C.c_float(0)
+        self._check(N.lib().fe_debug_h2d_probe(self._ctx, _ptr(host_array), host_array.nbytes, C.byref(ms)))
+        return float(ms.value)
+
     def forceGridClustering(self, enable=True):
         """Test hook: K2 through the grid-based kernels only (the run-based kernel's fallback and cross-check)."""
         self._check(N.lib().fe_debug_force_grid_clustering(self._ctx, 1 if enable else 0))

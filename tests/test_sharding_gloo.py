@@ -33,10 +33,28 @@ def _worker(rank, world, port, q):
     ko, kp, d, _ = ob.process_batch(P, p, o, r, mode=1, n_threads=1)
     res = gather_results(ko, kp, d)
     dist.barrier()
+    # the shared-memory form of the same gather (what bench.py times for config 5), twice: the second call
+    # reuses the segment, and a call without descriptors must work too
+    os.environ["MASTER_PORT"] = str(port)
+    from feature_extraction_b200.sharding import SharedGather
+    sg = SharedGather(tag="fe_gather_test")
+    res2 = sg.gather(ko, kp, d)
+    if rank == 0:
+        res2 = tuple(np.array(x) for x in res2)
+    res3 = sg.gather(ko, kp, d)
+    if rank == 0:
+        res3 = tuple(np.array(x) for x in res3)
+    res4 = sg.gather(ko, kp, None)
+    if rank == 0:
+        res4 = (np.array(res4[0]), np.array(res4[1]), res4[2])
+    sg.close()
     if rank == 0:
         ko_a, kp_a, d_a, _ = ob.process_batch(P, pts, offs, rp, mode=1, n_threads=1)
-        ok = (np.array_equal(res[0], ko_a) and np.array_equal(res[1].view(np.uint32), kp_a.view(np.uint32))
-              and np.array_equal(res[2].view(np.uint32), d_a.view(np.uint32)))
+        ok = True
+        for r3 in (res, res2, res3):
+            ok = ok and (np.array_equal(r3[0], ko_a) and np.array_equal(r3[1].view(np.uint32), kp_a.view(np.uint32))
+                         and np.array_equal(r3[2].view(np.uint32), d_a.view(np.uint32)))
+        ok = ok and np.array_equal(res4[0], ko_a) and np.array_equal(res4[1].view(np.uint32), kp_a.view(np.uint32)) and res4[2] is None
         q.put(bool(ok))
     dist.destroy_process_group()
 
