@@ -189,7 +189,7 @@ def stage_bytes(st, desc_len=1980):
         "K2 ring clusters": 20 * Nc + 16 * Kf,
         "K3 merge keypoints": 16 * Kf + 16 * K,
         "keypoint CSR": 32 * K,
-        "K4a surface grid": 16 * Ns + 16 * Ns,
+        "K4a surface grid": 16 * Ns + 16 * st.get("halo_points", Ns),  # read the surface stream, keep the points a keypoint can reach
         "K4b mark neighbours": 16 * M + 4 * M,
         "K4c density": 20 * M,
         "K4d shape context": 20 * M + 4 * desc_len * K,

@@ -38,6 +38,9 @@ struct Slot {
   int *d_kpNbrOff = nullptr, *d_kpRank = nullptr;  // K4b -> K4d: slice of the neighbour pool (d_keyA), RNG rank
   int *d_kpListM = nullptr, *d_kpListL = nullptr;  // keypoints of K4d's medium / large instantiation
   int *d_rowStart = nullptr, *d_surfN = nullptr, *d_perScan = nullptr, *d_outOff = nullptr;
+  int *d_perScan2 = nullptr, *d_outOff2 = nullptr;   // cloud outputs: ~keypoint_cloud counts / offsets
+  float4* d_gather2 = nullptr;
+  int *h_cloudOff = nullptr, *h_kcOff = nullptr;     // pinned: per-scan offsets of the two cloud outputs of the sub-batch
   unsigned short* d_cellTab = nullptr;
   int* d_tabOk = nullptr;
   int64_t capCellTab = 0;
@@ -96,9 +99,10 @@ struct fe_ctx {
   fe_point_t* h_kp = nullptr;
   float* h_desc = nullptr;
   int64_t capResKp = 0, capResDesc = 0;
-  // optional cloud outputs of the last single-sub-batch call
+  // optional cloud outputs of the last host batch call (fe_enable_cloud_outputs): CSR by scan, pinned
   std::vector<int64_t> cloudOff, kcOff;
-  std::vector<fe_point_t> cloudPts, kcPts;
+  fe_point_t *h_cloud = nullptr, *h_kc = nullptr;
+  int64_t capCloud = 0, capKcRes = 0, cloudRun = 0, kcRun = 0;
   // stage times of the last device call
   std::vector<const char*> stName;
   std::vector<float> stMs;
@@ -196,6 +200,7 @@ void surface_grid(DevParams& dp, double R, float x0, float x1, float y0, float y
   dp.sg_bx = std::max(1, bits_for_host(dp.sg_nx - 1));
   dp.Rpad = (float)(R * 1.0001 + 1e-6);
   dp.rhopad = (float)(rrho * 1.0001 + 1e-6);
+  dp.halopad = (float)((R + rrho) * 1.0002 + 4e-6);
 }
 
 int derive_params(fe_ctx* ctx, const fe_params_t& p) {
@@ -238,9 +243,9 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_ringPts, s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_perScan2, s.d_outOff2, s.d_gather2};
   for (void* p : dv) if (p) cudaFree(p);
-  void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd};
+  void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
   for (void* p : hv) if (p) cudaFreeHost(p);
   for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
   if (s.evDone) cudaEventDestroy(s.evDone);
@@ -387,6 +392,11 @@ int ensure_kc(fe_ctx* ctx, Slot& s) {
     s.capKc = (int)std::min<int64_t>(s.capPts, 1 << 26);
     CK(dalloc(&s.d_kcPool, (size_t)s.capKc));
     CK(dalloc(&s.d_gather, (size_t)s.capPts));
+    CK(dalloc(&s.d_gather2, (size_t)s.capKc));
+    CK(dalloc(&s.d_perScan2, (size_t)s.capScans));
+    CK(dalloc(&s.d_outOff2, (size_t)s.capScans + 1));
+    CK(halloc(&s.h_cloudOff, (size_t)s.capScans + 1));
+    CK(halloc(&s.h_kcOff, (size_t)s.capScans + 1));
   }
   return FE_OK;
 }
@@ -403,10 +413,11 @@ int set_kernel_attrs(fe_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
   CK(cudaFuncSetAttribute(k_extract_clusters_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
-  CK(cudaFuncSetAttribute(k_desc_hist<256, DCAP, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)desc_smem_bytes(DCAP, 256)));
-  CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_M, DCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CK(cudaFuncSetAttribute(k_desc_hist_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)desc_warp_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_desc_hist<256, DCAP, DW_CAP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)desc_smem_bytes(DCAP, 256)));
+  CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_M, DCAP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)desc_smem_bytes(DCAP_M, 512)));
-  CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_L, DCAP_M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CK(cudaFuncSetAttribute(k_desc_hist<512, DCAP_L, DCAP_M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)desc_smem_bytes(DCAP_L, 512)));
   CK(cudaFuncSetAttribute(k_surface_grid_cells<NT_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)surf_cells_smem_bytes(SURF_MAX_CELLS)));
@@ -421,17 +432,30 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
   // the blocks stride over the keypoints with equal shares: grids of exactly one resident wave
   static const int perSm = []() {  // initialised once, also when fe_multi's threads get here together
     int v = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist<256, DCAP, 0, false>, 256, desc_smem_bytes(DCAP, 256)) != cudaSuccess) v = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist<256, DCAP, DW_CAP, false, true>, 256, desc_smem_bytes(DCAP, 256)) != cudaSuccess) v = 4;
     return v;
   }();
+  {  // keypoints with at most DW_CAP listed neighbours (and the empty ones): a warp each
+    static const int perSmW = []() {
+      int v = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist_warp, DW_WARPS * 32, desc_warp_smem_bytes()) != cudaSuccess) v = 2;
+      return v;
+    }();
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    k_desc_hist_warp<<<nsm * std::max(perSmW, 1), DW_WARPS * 32, desc_warp_smem_bytes(), s.stream>>>(
+        s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap,
+        s.d_keyA, s.d_kpNbrOff, s.d_kpRank, s.d_desc, descStride, descOff, s.d_ctr);
+    ctx->launches++;
+  }
 #define FE_DESC_LIST nullptr, nullptr
-  k_desc_hist<256, DCAP, 0, false><<<std::min(gridKp, 148 * std::max(perSm, 1)), 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<256, DCAP, DW_CAP, false, true><<<std::min(gridKp, 148 * std::max(perSm, 1)), 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
 #define FE_DESC_LIST s.d_kpListM, &s.d_ctr->n_list_m
-  k_desc_hist<512, DCAP_M, DCAP, false><<<std::min(gridKp, 148 * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<512, DCAP_M, DCAP, false, false><<<std::min(gridKp, 148 * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
 #define FE_DESC_LIST s.d_kpListL, &s.d_ctr->n_list_l
-  k_desc_hist<512, DCAP_L, DCAP_M, true><<<std::min(gridKp, 148), 512, desc_smem_bytes(DCAP_L, 512), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<512, DCAP_L, DCAP_M, true, false><<<std::min(gridKp, 148), 512, desc_smem_bytes(DCAP_L, 512), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
 #undef FE_DESC_ARGS
   ctx->launches += 3;
@@ -464,18 +488,24 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, c
   const int ncells = P.sg_nx * P.sg_ny;
   if (ncells <= SURF_MAX_CELLS) {
     k_surface_grid_cells<NT_SURF><<<nscans, NT_SURF, surf_cells_smem_bytes(ncells), q>>>(
-        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf,
-        s.d_cellTab, s.d_tabOk);
+        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_kpOut, s.d_kpOff, s.d_sorted, s.d_rho, s.d_rowStart,
+        s.d_surfN, s.d_ctr, s.d_ovfSurf, s.d_cellTab, s.d_tabOk);
     k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
                                                                    s.d_keyB, s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey,
                                                                    s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf,
-                                                                   s.d_tabOk);
+                                                                   s.d_tabOk, s.d_rho);
   } else {
     k_surface_grid<<<nscans, NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA, s.d_keyB, s.d_valA,
                                                  s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, nullptr, nullptr,
-                                                 s.d_tabOk);
+                                                 s.d_tabOk, s.d_rho);
   }
   ctx->launches += 2;
+}
+
+void launch_density(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
+  if (nscans <= 0) return;
+  k_density<<<nscans, 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, s.d_surfN, s.d_rho, s.d_ctr->dens_work);
+  ctx->launches++;
 }
 
 // K2 + K3 for `nscans` scans: the 2-blocks-per-SM instantiation first, then the large one over
@@ -597,17 +627,6 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     int st = ensure_rowstart(ctx, s, nscans);
     if (st) return st;
   }
-  if (doDesc && !ctx->stageTiming) {
-    // K4a (HBM-bound) needs K1's surface stream only: it runs on the side stream while K2/K3 (latency /
-    // issue bound, little HBM traffic) occupy the main one, and is joined before K4b.  With stage timing
-    // on, the stages run one after the other instead, so that every event pair brackets one stage alone.
-    CK(cudaEventRecord(s.evFork, s.stream));
-    CK(cudaStreamWaitEvent(s.stream2, s.evFork, 0));
-    CK(cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(npts, 1) * sizeof(int), s.stream2));
-    launch_surface_grid(ctx, s, nscans, P, s.stream2);
-    CK(cudaEventRecord(s.evJoin, s.stream2));
-    s.sideK4a = true;
-  }
   launch_clustering(ctx, s, nscans, singleRing, wantKc, true, true);
   mark(ctx, s, "K3 merge keypoints");
   if (bnd) {
@@ -621,13 +640,9 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
   ctx->launches++;
   mark(ctx, s, "keypoint CSR");
   if (doDesc) {
-    if (s.sideK4a) {
-      CK(cudaStreamWaitEvent(s.stream, s.evJoin, 0));
-    } else {
-      CK(cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(npts, 1) * sizeof(int), s.stream));
-      launch_surface_grid(ctx, s, nscans, P, s.stream);
-      mark(ctx, s, "K4a surface grid");
-    }
+    // K4a runs after the keypoints are known: it only keeps the surface points a keypoint can reach
+    launch_surface_grid(ctx, s, nscans, P, s.stream);
+    mark(ctx, s, "K4a surface grid");
     const int gridKp = 148 * 8;
     launch_desc_mark(ctx, s, nscans, P, gridKp);
     mark(ctx, s, "K4b mark neighbours");
@@ -635,18 +650,28 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
       k_boundary_support<<<148 * 4, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, surf_index(ctx, s),
                                                          s.d_scan_off, P, boundary_spec(ctx), s.d_bnd);
       if (npts > 0)
-        k_boundary_density<<<(int)std::min<int64_t>((npts + 255) / 256, 148 * 64), 256, 0, s.stream>>>(
-            s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, (long long)npts, s.d_rho, boundary_spec(ctx), s.d_bnd);
+        k_boundary_density<<<nscans, 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, s.d_surfN, s.d_rho,
+                                                         boundary_spec(ctx), s.d_bnd);
       ctx->launches += 2;
     }
-    if (npts > 0) {
-      const int gridD = (int)std::min<int64_t>((npts + 255) / 256, 148 * 64);
-      k_density<<<gridD, 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, (long long)npts, s.d_rho);
-      ctx->launches++;
-    }
+    launch_density(ctx, s, nscans, P);
     mark(ctx, s, "K4c density");
     launch_desc_hist(ctx, s, nscans, P, gridKp, ctx->recordOutput);
     mark(ctx, s, "K4d shape context");
+  }
+  if (wantKc && ctx->cloudOutputs && nscans > 0) {
+    // ~cloud (src:137-139) and ~keypoint_cloud (src:133-135): per-scan counts, offsets and the ordered gather all
+    // on the device; the host only learns the offsets (finalize_subbatch then copies the dense arrays out)
+    const int gb = (nscans + 255) / 256;
+    k_piece_counts<<<gb, 256, 0, s.stream>>>(s.d_cropCnt, s.d_chunk_off, nscans, s.d_perScan);
+    k_offsets_scan<<<1, 1024, 0, s.stream>>>(s.d_perScan, nscans, s.d_outOff);
+    k_gather_chunks<<<nscans, 256, 0, s.stream>>>(s.d_crop, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, s.d_outOff, s.d_gather);
+    k_pool16_counts<<<gb, 256, 0, s.stream>>>(s.d_kcCnt, nscans, s.d_perScan2);
+    k_offsets_scan<<<1, 1024, 0, s.stream>>>(s.d_perScan2, nscans, s.d_outOff2);
+    k_gather_pool16<<<nscans, 256, 0, s.stream>>>(s.d_kcPool, s.d_kcBase, s.d_kcCnt, s.d_outOff2, s.d_gather2);
+    ctx->launches += 6;
+    CK(cudaMemcpyAsync(s.h_cloudOff, s.d_outOff, (size_t)(nscans + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.h_kcOff, s.d_outOff2, (size_t)(nscans + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   }
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaMemcpyAsync(s.h_kpOff, s.d_kpOff, (size_t)(nscans + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
@@ -689,6 +714,18 @@ int grow_results(fe_ctx* ctx, int64_t needKp, bool desc) {
   return FE_OK;
 }
 
+int grow_pinned_points(fe_ctx* ctx, fe_point_t** buf, int64_t* cap, int64_t used, int64_t need) {
+  if (need <= *cap) return FE_OK;
+  for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
+  const int64_t ncap = std::max<int64_t>(need * 3 / 2, 1 << 16);
+  fe_point_t* nb = nullptr;
+  CK(halloc(&nb, (size_t)ncap));
+  if (*buf) { memcpy(nb, *buf, (size_t)used * sizeof(fe_point_t)); cudaFreeHost(*buf); }
+  *buf = nb;
+  *cap = ncap;
+  return FE_OK;
+}
+
 // wait for the sub-batch in `s`, check its error word, append its keypoints to the results
 int finalize_subbatch(fe_ctx* ctx, Slot& s, int64_t& kpRun, bool desc) {
   if (!s.busy) return FE_OK;
@@ -707,6 +744,21 @@ int finalize_subbatch(fe_ctx* ctx, Slot& s, int64_t& kpRun, bool desc) {
     if (desc) CK(cudaMemcpyAsync(ctx->h_desc + kpRun * dl, s.d_desc, (size_t)K * dl * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
   }
   kpRun += K;
+  if (ctx->cloudOutputs && s.h_cloudOff) {  // the two optional clouds, gathered on the device by enqueue_pipeline
+    const int64_t tc = s.h_cloudOff[s.nscans], tk = s.h_kcOff[s.nscans];
+    st = grow_pinned_points(ctx, &ctx->h_cloud, &ctx->capCloud, ctx->cloudRun, ctx->cloudRun + tc);
+    if (st) return st;
+    st = grow_pinned_points(ctx, &ctx->h_kc, &ctx->capKcRes, ctx->kcRun, ctx->kcRun + tk);
+    if (st) return st;
+    for (int i = 0; i <= s.nscans; i++) {
+      ctx->cloudOff[s.firstScan + i] = ctx->cloudRun + s.h_cloudOff[i];
+      ctx->kcOff[s.firstScan + i] = ctx->kcRun + s.h_kcOff[i];
+    }
+    if (tc > 0) CK(cudaMemcpyAsync(ctx->h_cloud + ctx->cloudRun, s.d_gather, (size_t)tc * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
+    if (tk > 0) CK(cudaMemcpyAsync(ctx->h_kc + ctx->kcRun, s.d_gather2, (size_t)tk * sizeof(float4), cudaMemcpyDeviceToHost, s.stream));
+    ctx->cloudRun += tc;
+    ctx->kcRun += tk;
+  }
   return FE_OK;
 }
 
@@ -861,6 +913,8 @@ void fe_destroy(fe_ctx_t* ctx) {
   if (ctx->d_axes) cudaFree(ctx->d_axes);
   if (ctx->h_kp) cudaFreeHost(ctx->h_kp);
   if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+  if (ctx->h_cloud) cudaFreeHost(ctx->h_cloud);
+  if (ctx->h_kc) cudaFreeHost(ctx->h_kc);
   delete ctx;
 }
 
@@ -929,11 +983,11 @@ int fe_debug_libm_f32(fe_ctx_t* ctx, int32_t op, const float* a, const float* b,
 int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_point_t** cloud,
                          const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud) {
   if (!ctx) return FE_ERR_INVALID;
-  if (ctx->cloudOff.empty()) return fail(ctx, FE_ERR_INVALID, "no cloud outputs recorded (enable them before a single-sub-batch call)");
+  if (ctx->cloudOff.empty()) return fail(ctx, FE_ERR_INVALID, "no cloud outputs recorded (fe_enable_cloud_outputs before fe_process_batch)");
   if (cloud_offsets) *cloud_offsets = ctx->cloudOff.data();
-  if (cloud) *cloud = ctx->cloudPts.data();
+  if (cloud) *cloud = ctx->h_cloud;
   if (kpcloud_offsets) *kpcloud_offsets = ctx->kcOff.data();
-  if (keypoint_cloud) *keypoint_cloud = ctx->kcPts.data();
+  if (keypoint_cloud) *keypoint_cloud = ctx->h_kc;
   return FE_OK;
 }
 
@@ -958,7 +1012,9 @@ static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int st
   const int64_t launches0 = ctx->launches;
   ctx->kpOffsets.assign((size_t)n_scans + 1, 0);
   ctx->bndCounts.assign(ctx->bndEps > 0.0 ? (size_t)n_scans * 4 : 0, 0);
-  ctx->cloudOff.clear(); ctx->kcOff.clear(); ctx->cloudPts.clear(); ctx->kcPts.clear();
+  ctx->cloudOff.clear(); ctx->kcOff.clear();
+  ctx->cloudRun = ctx->kcRun = 0;
+  if (ctx->cloudOutputs) { ctx->cloudOff.assign((size_t)n_scans + 1, 0); ctx->kcOff.assign((size_t)n_scans + 1, 0); }
   int64_t kpRun = 0;
   int first = 0, cur = 0;
   int nsub = 0;
@@ -1006,16 +1062,7 @@ static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int st
     if (st) return st;
   }
   for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
-  if (nsub == 1) {
-    Slot& s = ctx->slot[0];
-    collect_times(ctx, s);
-    if (ctx->cloudOutputs) {
-      int st = gather_to_host(ctx, s, s.nscans, true, s.d_crop, s.d_cropCnt, nullptr, ctx->cloudOff, ctx->cloudPts);
-      if (st) return st;
-      st = gather_to_host(ctx, s, s.nscans, false, s.d_kcPool, s.d_kcCnt, s.d_kcBase, ctx->kcOff, ctx->kcPts);
-      if (st) return st;
-    }
-  }
+  if (nsub == 1) collect_times(ctx, ctx->slot[0]);
   out->n_scans = n_scans;
   out->n_keypoints = kpRun;
   out->keypoint_offsets = ctx->kpOffsets.data();
@@ -1387,16 +1434,11 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
   if (cudaMemsetAsync(s.d_ctr, 0, sizeof(DevCounters), q) != cudaSuccess ||
       cudaMemcpyAsync(s.d_kpOff, kpOff.data(), 2 * sizeof(int), cudaMemcpyHostToDevice, q) != cudaSuccess ||
       cudaMemcpyAsync(s.d_kpScan, kpScan.data(), (size_t)k * sizeof(int), cudaMemcpyHostToDevice, q) != cudaSuccess ||
-      cudaMemcpyAsync(s.d_kpOut, keypoints, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, q) != cudaSuccess ||
-      cudaMemsetAsync(s.d_rho, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(int), q) != cudaSuccess)
+      cudaMemcpyAsync(s.d_kpOut, keypoints, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, q) != cudaSuccess)
     return restore(fail(ctx, FE_ERR_CUDA, "staging of the descriptor inputs failed"));
   launch_surface_grid(ctx, s, 1, P, s.stream);
   launch_desc_mark(ctx, s, 1, P, 148 * 4);
-  if (n > 0) {
-    k_density<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 64), 256, 0, q>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P,
-                                                                               (long long)n, s.d_rho);
-    ctx->launches++;
-  }
+  launch_density(ctx, s, 1, P);
   launch_desc_hist(ctx, s, 1, P, 148 * 4, false);
   ctx->dp = saved;
   CK(cudaGetLastError());
@@ -1425,6 +1467,9 @@ int fe_pack_point_descriptors(const fe_point_t* keypoints, const float* descript
 struct fe_multi {
   std::vector<fe_ctx_t*> ctx;
   std::vector<int64_t> kpOffsets;
+  bool cloudOutputs = false;
+  std::vector<int64_t> cloudOff, kcOff;
+  std::vector<fe_point_t> cloudPts, kcPts;
   fe_point_t* kp = nullptr;   // gathered results: plain malloc'd buffers grown on demand (no zero fill)
   float* desc = nullptr;
   int64_t capKp = 0, capDesc = 0;
@@ -1452,6 +1497,27 @@ int fe_multi_enable_record_output(fe_multi_t* m, int32_t enable) {
     const int st = fe_enable_record_output(c, enable);
     if (st) return st;
   }
+  return FE_OK;
+}
+
+int fe_multi_enable_cloud_outputs(fe_multi_t* m, int32_t enable) {
+  if (!m) return FE_ERR_INVALID;
+  for (fe_ctx_t* c : m->ctx) {
+    const int st = fe_enable_cloud_outputs(c, enable);
+    if (st) return st;
+  }
+  m->cloudOutputs = enable != 0;
+  return FE_OK;
+}
+
+int fe_multi_get_cloud_outputs(fe_multi_t* m, const int64_t** cloud_offsets, const fe_point_t** cloud,
+                               const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud) {
+  if (!m) return FE_ERR_INVALID;
+  if (m->cloudOff.empty()) { m->err = "no cloud outputs recorded (fe_multi_enable_cloud_outputs before fe_multi_process_batch)"; return FE_ERR_INVALID; }
+  if (cloud_offsets) *cloud_offsets = m->cloudOff.data();
+  if (cloud) *cloud = m->cloudPts.data();
+  if (kpcloud_offsets) *kpcloud_offsets = m->kcOff.data();
+  if (keypoint_cloud) *keypoint_cloud = m->kcPts.data();
   return FE_OK;
 }
 
@@ -1520,6 +1586,23 @@ int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_
       });
     for (auto& t : th) t.join();
   }
+  m->cloudOff.clear(); m->kcOff.clear();
+  if (m->cloudOutputs) {  // the shards' ~cloud / ~keypoint_cloud concatenated in scan order
+    m->cloudOff.assign((size_t)n_scans + 1, 0); m->kcOff.assign((size_t)n_scans + 1, 0);
+    m->cloudPts.clear(); m->kcPts.clear();
+    for (int g = 0; g < G; g++) {
+      const int ns = lo[g + 1] - lo[g];
+      if (ns == 0) continue;
+      const int64_t *co = nullptr, *ko = nullptr;
+      const fe_point_t *cp = nullptr, *kp2 = nullptr;
+      const int st = fe_get_cloud_outputs(m->ctx[g], &co, &cp, &ko, &kp2);
+      if (st != FE_OK) { m->err = std::string("device shard ") + std::to_string(g) + ": " + fe_last_error(m->ctx[g]); return st; }
+      const int64_t cb = (int64_t)m->cloudPts.size(), kb = (int64_t)m->kcPts.size();
+      for (int i = 0; i <= ns; i++) { m->cloudOff[lo[g] + i] = cb + co[i]; m->kcOff[lo[g] + i] = kb + ko[i]; }
+      m->cloudPts.insert(m->cloudPts.end(), cp, cp + co[ns]);
+      m->kcPts.insert(m->kcPts.end(), kp2, kp2 + ko[ns]);
+    }
+  }
   out->n_scans = n_scans;
   out->n_keypoints = K;
   out->keypoint_offsets = m->kpOffsets.data();
@@ -1528,6 +1611,24 @@ int fe_multi_process_batch(fe_multi_t* m, const fe_point_t* points, const int64_
   out->on_device = 0;
   out->gpu_launches = 0;
   for (int g = 0; g < G; g++) out->gpu_launches += res[g].gpu_launches;
+  return FE_OK;
+}
+
+// bench hook: work of the 3DSC density stage of the last device call: out = {distance tests, marked surface points
+// (distinct points inside some keypoint's support sphere), halo points kept by the cell grid}
+int fe_debug_density_work(fe_ctx_t* ctx, int64_t out[3]) {
+  if (!ctx || !out || !ctx->slot[0].stream) return FE_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  Slot& s = ctx->slot[0];
+  CK(cudaStreamSynchronize(s.stream));
+  out[0] = (int64_t)s.h_ctr->dens_work[0];
+  out[1] = (int64_t)s.h_ctr->dens_work[1];
+  out[2] = 0;
+  if (s.nscans > 0 && ctx->params.estimate_descriptors) {
+    std::vector<int> sn((size_t)s.nscans);
+    CK(cudaMemcpy(sn.data(), s.d_surfN, sn.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int v : sn) out[2] += v;
+  }
   return FE_OK;
 }
 

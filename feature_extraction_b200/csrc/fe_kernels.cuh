@@ -74,6 +74,7 @@ struct DevParams {
   int min_channels;
   // 3DSC
   float R2f, rho2f, Rpad, rhopad;
+  float halopad;  // R + R/5 padded: only surface points this close (in x and in y) to a keypoint can matter
   float radii[16], theta[12], phi[13];
   int estimate_descriptors;
   int angle_libm;  // 0: fdlibm atan2f/acosf (glibc <= 2.40), 1: correctly rounded (glibc >= 2.41)
@@ -94,8 +95,9 @@ struct DevCounters {
   int pad[1];
   unsigned long long nbr_cursor;  // neighbour-list pool (K4b -> K4d)
   int kd_cursor;                  // next keypoint batch of the fast K4d instantiation
+  int kw_cursor;                  // next keypoint of the warp-per-keypoint K4d
   int n_list_m, n_list_l;         // keypoints listed for the medium / large K4d instantiation
-  int pad2;
+  unsigned long long dens_work[2];  // K4c: distance tests, marked points
 };
 
 // getElevationAngles, src:147-156, literally: double atan2 / cos / sin / atan2.
@@ -1193,6 +1195,21 @@ __global__ void __launch_bounds__(256) k_gather_pool16(
   }
 }
 
+// exclusive prefix of n counts (one block): off[0..n], off[n] = total
+__global__ void __launch_bounds__(1024) k_offsets_scan(const int* __restrict__ cnt, int n, int* __restrict__ off) {
+  __shared__ int sc[40];
+  int run = 0;
+  for (int s0 = 0; s0 < n; s0 += 1024) {
+    const int s = s0 + threadIdx.x;
+    const int v = (s < n) ? cnt[s] : 0;
+    int tot;
+    const int pos = block_excl_scan<1024>(v, &tot, sc);
+    if (s < n) off[s] = run + pos;
+    run += tot;
+  }
+  if (threadIdx.x == 0) off[n] = run;
+}
+
 __global__ void k_pool16_counts(const int* __restrict__ pCnt, int n_scans, int* __restrict__ perScan) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_scans) return;
@@ -1223,7 +1240,7 @@ __device__ void surface_grid_scan_global(
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, const DevParams& P,
     unsigned* __restrict__ keyA, unsigned* __restrict__ keyB, unsigned* __restrict__ valA,
     unsigned* __restrict__ valB, float4* __restrict__ sorted, unsigned* __restrict__ sortedKey,
-    int* __restrict__ rowStart, int* __restrict__ surfN, DevCounters* __restrict__ ctr) {
+    int* __restrict__ rowStart, int* __restrict__ surfN, DevCounters* __restrict__ ctr, int* __restrict__ rho) {
   int* pre = M.pre;
   int* sc = M.sc;
   unsigned* wc = M.wc;
@@ -1241,6 +1258,7 @@ __device__ void surface_grid_scan_global(
   }
   unsigned* kA = keyA + base; unsigned* kB = keyB + base;
   unsigned* vA = valA + base; unsigned* vB = valB + base;
+  for (int i = tid; i < n; i += NT2) rho[base + i] = 0;
   for (int i = tid; i < n; i += NT2) {
     const long long pp = piece_pos(pre, nch, i, base);
     const float4 q = surf[pp];
@@ -1280,19 +1298,19 @@ __global__ void __launch_bounds__(NT2, 2) k_surface_grid(
     unsigned* __restrict__ keyA, unsigned* __restrict__ keyB, unsigned* __restrict__ valA,
     unsigned* __restrict__ valB, float4* __restrict__ sorted, unsigned* __restrict__ sortedKey,
     int* __restrict__ rowStart, int* __restrict__ surfN, DevCounters* __restrict__ ctr,
-    const int* __restrict__ scanList, const int* __restrict__ nList, int* __restrict__ tabOk) {
+    const int* __restrict__ scanList, const int* __restrict__ nList, int* __restrict__ tabOk, int* __restrict__ rho) {
   __shared__ SurfGlobalSm M;
   if (!scanList) {
     if (threadIdx.x == 0) tabOk[blockIdx.x] = 0;
     surface_grid_scan_global(M, blockIdx.x, surf, surfCnt, scan_off, chunk_off, P, keyA, keyB, valA, valB, sorted, sortedKey,
-                             rowStart, surfN, ctr);
+                             rowStart, surfN, ctr, rho);
   } else {
     const int n = *nList;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
       __syncthreads();
       if (threadIdx.x == 0) tabOk[scanList[i]] = 0;
       surface_grid_scan_global(M, scanList[i], surf, surfCnt, scan_off, chunk_off, P, keyA, keyB, valA, valB, sorted,
-                               sortedKey, rowStart, surfN, ctr);
+                               sortedKey, rowStart, surfN, ctr, rho);
     }
   }
 }
@@ -1305,17 +1323,30 @@ __global__ void __launch_bounds__(NT2, 2) k_surface_grid(
 // Scans with more than 65,535 surface points (16-bit counters) are deferred to the radix kernel.
 constexpr int NT_SURF = 512;           // threads of the counting-sort K4a (384 was measured: slower)
 constexpr int SURF_MAX_CELLS = 57344;  // 112 KB of counters: 2 blocks / SM at the upper end
-constexpr size_t surf_cells_smem_bytes(int ncells) { return (size_t)((ncells + 1) / 2) * 4 + 64; }
+constexpr size_t surf_cells_smem_bytes(int ncells) {
+  return (size_t)((((ncells + 1) / 2) + 3) & ~3) * 4 + 64 + (size_t)((ncells + 31) / 32) * 4 + 16;  // counters + halo bit map
+}
 
+// The cell grid only ever serves the 3DSC stage, and that only looks at surface points within R of a
+// keypoint (support) or within R + R/5 (density of the support points).  The kernel therefore runs after
+// the keypoints are known and keeps only the points of HALO cells — cells a keypoint's box of half-width
+// R + R/5 touches (a bit map in shared memory) — which is a few percent of a sparse scan.  Scans without
+// keypoints are not read at all.  (Ordering every cell by z so that the density sweep could binary-search
+// its z window was built and measured: 2x fewer distance tests, but the searches and the data-dependent
+// loop ends cost more than the tests they saved — K4c 0.90 -> 1.02 ms on config 2, 15.7 -> 33.9 ms on
+// config 3 — so the order inside a cell stays free.)
 template <int NTS>
 __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     const float4* __restrict__ surf, const int* __restrict__ surfCnt,
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
-    float4* __restrict__ sorted, unsigned* __restrict__ sortedKey, int* __restrict__ rowStart,
+    const float4* __restrict__ kpOut, const int* __restrict__ kpOff,
+    float4* __restrict__ sorted, int* __restrict__ rho, int* __restrict__ rowStart,
     int* __restrict__ surfN, DevCounters* __restrict__ ctr, int* __restrict__ ovfList,
     unsigned short* __restrict__ cellTab, int* __restrict__ tabOk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned* cells = (unsigned*)smem_raw;  // packed pairs of 16-bit counters / cursors
+  const int nx = P.sg_nx, ny = P.sg_ny, ncells = nx * ny, nwords = (ncells + 1) / 2, nbm = (ncells + 31) / 32;
+  unsigned* cells = (unsigned*)smem_raw;        // packed pairs of 16-bit counters / cursors
+  unsigned* halo = cells + ((nwords + 3) & ~3) + 16;  // one bit per cell
   __shared__ int sc[40];
   __shared__ int s_n;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -1323,9 +1354,13 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
   const long long base = scan_off[s];
   const int c0 = chunk_off[s];
   const int nch = chunk_off[s + 1] - c0;
-  const int nx = P.sg_nx, ny = P.sg_ny, ncells = nx * ny, nwords = (ncells + 1) / 2;
   int* rs = rowStart + (long long)s * (ny + 1);
-  // total surface points of the scan
+  const int k0 = kpOff[s], k1 = kpOff[s + 1];
+  if (k1 == k0) {  // no keypoint: nothing of this scan's surface is ever looked at
+    if (tid == 0) { surfN[s] = 0; tabOk[s] = 1; }
+    return;
+  }
+  // total surface points of the scan (the 16-bit counters hold at most 65,535 of them)
   {
     int v = 0;
     for (int c = tid; c < nch; c += NTS) v += surfCnt[c0 + c];
@@ -1333,28 +1368,34 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     block_excl_scan<NTS>(v, &tot, sc);
     if (tid == 0) s_n = tot;
   }
-  for (int i = tid; i < (nwords + 3) / 4; i += NTS) ((uint4*)cells)[i] = make_uint4(0u, 0u, 0u, 0u);  // 64 bytes of slack follow
+  for (int i = tid; i < (nwords + 3) / 4; i += NTS) ((uint4*)cells)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < nbm; i += NTS) halo[i] = 0u;
   __syncthreads();
-  const int n = s_n;
-  if (n > 65535) {
+  if (s_n > 65535) {
     if (tid == 0) { ovfList[atomicAdd(&ctr->ovf_surf, 1)] = s; tabOk[s] = 0; }
     return;
   }
-  if (tid == 0) { surfN[s] = n; tabOk[s] = 1; }
+  // (0) halo cells: a warp per keypoint, lanes over the cells of its box
+  for (int k = k0 + w; k < k1; k += NW) {
+    const float4 o = kpOut[k];
+    if (!finite3(o.x, o.y, o.z)) continue;
+    const int cx0 = surf_cell(o.x - P.halopad, P.sx0, P.sg_inv, nx), cx1 = surf_cell(o.x + P.halopad, P.sx0, P.sg_inv, nx);
+    const int cy0 = surf_cell(o.y - P.halopad, P.sy0, P.sg_inv, ny), cy1 = surf_cell(o.y + P.halopad, P.sy0, P.sg_inv, ny);
+    const int bw = cx1 - cx0 + 1, nb = bw * (cy1 - cy0 + 1);
+    for (int t = lane; t < nb; t += 32) {
+      const int cell = (cy0 + t / bw) * nx + cx0 + t % bw;
+      atomicOr(&halo[cell >> 5], 1u << (cell & 31));
+    }
+  }
+  __syncthreads();
   const int tabStride = (ncells + 2) & ~1;  // even: every scan's table is 4-byte aligned
   unsigned short* tab = cellTab + (long long)s * tabStride;
-  if (n == 0) {
-    for (int r = tid; r <= ny; r += NTS) rs[r] = 0;
-    for (int i = tid; i <= ncells; i += NTS) tab[i] = 0;
-    return;
-  }
-  // (1) count: the survivors of a chunk are contiguous; the chunks are cut into runs of 128 points that
-  //     are dealt to the warps (a scan has fewer chunks than the block has warps)
+  // (1) count: the survivors of a chunk are contiguous; the chunks are cut into runs of 256 points that
+  //     are dealt to the warps, eight loads in flight per lane (only x and y are needed here)
   for (int it = w; it < nch * (CH / 256); it += NW) {
     const int c = it / (CH / 256);
     const int j1 = surfCnt[c0 + c];
     const float4* src = surf + base + (long long)c * CH;
-    // eight loads in flight per lane (only x and y are needed here): the sweep is latency-bound
     const int j = (it % (CH / 256)) * 256 + lane;
     if (j - lane >= j1) continue;
     float2 q[8];
@@ -1364,7 +1405,7 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     for (int k = 0; k < 8; k++) {
       if (j + 32 * k < j1) {
         const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
-        atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
+        if ((halo[cell >> 5] >> (cell & 31)) & 1u) atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
       }
     }
   }
@@ -1383,8 +1424,11 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
       cells[i] = (unsigned)run | ((unsigned)(run + lo) << 16);  // starts of the two cells
       run += lo + hi;
     }
+    if (tid == 0) s_n = tot;  // halo points only
   }
   __syncthreads();
+  const int n = s_n;
+  if (tid == 0) { surfN[s] = n; tabOk[s] = 1; }
   for (int r = tid; r <= ny; r += NTS) {
     int v = n;
     if (r < ny) { const int cell = r * nx; const unsigned wv = cells[cell >> 1]; v = (cell & 1) ? (int)(wv >> 16) : (int)(wv & 0xFFFFu); }
@@ -1397,27 +1441,28 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     for (int i = tid; i < nwords; i += NTS) tabw[i] = cells[i];
     if (tid == 0 && (ncells & 1) == 0) tabw[nwords] = (unsigned)n;
   }
+  for (int i = tid; i < n; i += NTS) rho[base + i] = 0;  // K4b marks, K4c counts: only these slots are ever used
   __syncthreads();
-  // (3) scatter: the start of a cell doubles as its cursor (it ends at the cell's end <= n <= 65535,
-  //     so a 16-bit half never carries into its neighbour)
+  if (n == 0) return;
+  // (3) scatter: the start of a cell doubles as its cursor (it ends at the cell's end <= n <= 65535, so a
+  //     16-bit half never carries into its neighbour); the order inside a cell is free
   float4* so = sorted + base;
   for (int it = w; it < nch * (CH / 128); it += NW) {
     const int c = it / (CH / 128);
     const int j1 = surfCnt[c0 + c];
     const float4* src = surf + base + (long long)c * CH;
-    {
-      const int j = (it % (CH / 128)) * 128 + lane;
-      if (j - lane >= j1) continue;
-      float4 q[4];
+    const int j = (it % (CH / 128)) * 128 + lane;
+    if (j - lane >= j1) continue;
+    float4 q[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (j + 32 * k < j1) {
-          const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
+    for (int k = 0; k < 4; k++) {
+      if (j + 32 * k < j1) {
+        const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
+        if ((halo[cell >> 5] >> (cell & 31)) & 1u) {
           const unsigned old = atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
-          const int pos = (cell & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu);
-          so[pos] = q[k];  // no sorted key: scans with a cell table are never searched by key
+          so[(cell & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu)] = q[k];
         }
       }
     }
@@ -1560,34 +1605,75 @@ __global__ void __launch_bounds__(256) k_kp_rank(const int* __restrict__ kpScan,
 // K4c — local point density (3dsc.hpp: searchForNeighbors(point_density_radius_)), once per
 // marked surface point instead of once per (keypoint, neighbour) as PCL does.
 // ============================================================================================
+// One block per scan walks the scan's sorted (halo) points in tiles: the marked ones of a tile are
+// compacted into a list (they stay in cell order, so neighbouring lanes share cells and their loads hit
+// L1), then every thread takes one marked point and sweeps the three rows of cells its density sphere
+// touches (contiguous spans, fixed trip counts).
+constexpr int DENS_TILE = 1024;
 __global__ void __launch_bounds__(256) k_density(
     const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P,
-    long long total, int* __restrict__ rho) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = rho[i];
-    if (v >= 0) continue;
-    const int s = -v - 1;
-    const long long base = scan_off[s];
-    const float4* so = sorted + base;
-    const unsigned* sk = X.sortedKey + base;
-    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
-    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
-    const float4 p = sorted[i];
-    // cells reached by the density radius (>= 1 cell each way; more only if the grid was capped)
-    const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, P.sg_nx);
-    const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, P.sg_ny);
-    int cnt = 0;
-    for (int r = cy0; r <= cy1; r++) {
-      int b, e;
-      row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
-      for (int j = b; j < e; j++) {
-        const float4 q = so[j];
-        // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
-        if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
-      }
+    const int* __restrict__ surfN, int* __restrict__ rho, unsigned long long* __restrict__ tests) {
+  __shared__ unsigned short s_list[DENS_TILE];
+  __shared__ int s_wsum[8];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n = surfN[s];
+  if (n == 0) return;
+  const long long base = scan_off[s];
+  const float4* so = sorted + base;
+  int* rh = rho + base;
+  const unsigned* sk = X.sortedKey + base;
+  const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+  const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+  const int nx = P.sg_nx, ny = P.sg_ny;
+  unsigned ntest = 0, nmark = 0;  // per thread: at most 65,535 candidates per marked point, a few marked points
+  for (int t0 = 0; t0 < n; t0 += DENS_TILE) {
+    // marked points of the tile, in order
+    int cntw = 0;
+    unsigned mk[DENS_TILE / 256];
+#pragma unroll
+    for (int k = 0; k < DENS_TILE / 256; k++) {
+      const int i = t0 + (w * (DENS_TILE / 256) + k) * 32 + lane;  // a warp owns DENS_TILE/8 consecutive points
+      mk[k] = __ballot_sync(FE_FULL, i < n && rh[i] < 0);
+      cntw += __popc(mk[k]);
     }
-    rho[i] = cnt;
+    __syncthreads();  // the previous tile's list is no longer read
+    if (lane == 0) s_wsum[w] = cntw;
+    __syncthreads();
+    int off = 0, m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (k < w) off += s_wsum[k]; m += s_wsum[k]; }
+#pragma unroll
+    for (int k = 0; k < DENS_TILE / 256; k++) {
+      if ((mk[k] >> lane) & 1u) s_list[off + __popc(mk[k] & lanemask_lt())] = (unsigned short)((w * (DENS_TILE / 256) + k) * 32 + lane);
+      off += __popc(mk[k]);
+    }
+    __syncthreads();
+    for (int t = tid; t < m; t += 256) {
+      const int i = t0 + (int)s_list[t];
+      const float4 p = so[i];
+      // cells reached by the density radius (>= 1 cell each way; more only if the grid was capped)
+      const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, nx);
+      const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, ny);
+      int cnt = 0;
+      for (int r = cy0; r <= cy1; r++) {
+        int b, e;
+        row_span(sk, rs, ct, nx, r, cx0, cx1, P.sg_bx, b, e);
+        for (int j = b; j < e; j++) {
+          const float4 q = so[j];
+          // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
+          if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+        }
+        ntest += (unsigned)(e - b);
+      }
+      rh[i] = cnt;
+      nmark++;
+    }
+  }
+  if (tests) {  // work counters for the bench: marked points and distance tests
+    unsigned long long a = ntest, b = nmark;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { a += __shfl_xor_sync(FE_FULL, a, d); b += __shfl_xor_sync(FE_FULL, b, d); }
+    if (lane == 0 && b) { atomicAdd(&tests[0], a); atomicAdd(&tests[1], b); }
   }
 }
 
@@ -1670,7 +1756,7 @@ __device__ __forceinline__ bool shape_context_contribution(const float4 o, const
 // Three instantiations share the keypoints by neighbour count: (NB_MIN, CAP] each; the LAST one also
 // takes keypoints beyond its CAP, whose sums then use shared-memory float atomics (order-free,
 // ~1e-7 relative) and are counted in DevCounters::desc_unordered.
-template <int NT, int CAP, int NB_MIN, bool LAST>
+template <int NT, int CAP, int NB_MIN, bool LAST, bool DYN>
 __global__ void __launch_bounds__(NT) k_desc_hist(
     const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
     int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted, SurfIndex X,
@@ -1696,7 +1782,6 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
   // cost varies with the neighbour count; equal static shares left the slowest block ~40 % behind);
   // the next batch is requested before the current one is worked on.  The larger instantiations
   // stride over the list of their keypoints that k_kp_rank made.
-  constexpr bool DYN = (NB_MIN == 0);
   __shared__ int s_next;
   int g0 = blockIdx.x, gstep = gridDim.x, glen = 1;
   if (DYN) {
@@ -1713,8 +1798,8 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const int g = DYN ? gi : glist[gi];
     float* out = desc + (long long)g * descStride + descOff;
     const int nb = kpNbr[g];
-    if (NB_MIN > 0 && nb <= NB_MIN) continue;  // a smaller instantiation's keypoint
     if (!LAST && nb > CAP) continue;           // a larger instantiation's keypoint
+    if (NB_MIN > 0 && nb <= NB_MIN && (nb == 0 || kpNbrOff[g] >= 0)) continue;  // the warp kernel's keypoint
     if (nb == 0) {  // no neighbour (or non-finite keypoint): descriptor is NaN (3dsc.hpp)
       for (int i = tid; i < FE_DESC_LEN; i += NT) out[i] = __int_as_float(0x7fc00000);
       continue;
@@ -1799,7 +1884,12 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
         const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
         int bin; float wgt;
         if (shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wgt)) {
-          const int slot = atomicAdd(&s_cnt, 1);
+          // one slot reservation per warp-ful of contributions, not one atomic on the same word per lane
+          const unsigned act = __activemask();
+          const int leader = __ffs(act) - 1;
+          int slot = 0;
+          if (lane == leader) slot = atomicAdd(&s_cnt, __popc(act));
+          slot = __shfl_sync(act, slot, leader) + __popc(act & lanemask_lt());
           keyA[slot] = ((unsigned long long)bin << 52) | ((unsigned long long)__float_as_uint(d2) << 20) |
                        (unsigned long long)((unsigned)__float_as_int(q.w) & 0xFFFFFu);
           wA[slot] = wgt;
@@ -1872,6 +1962,111 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
   } else {
     g0 += gstep;
   }
+  }
+}
+
+// K4d for small neighbourhoods: ONE WARP per keypoint, no block barrier anywhere.  Keypoints with at most
+// DW_CAP neighbours whose list K4b left in the pool (and those with none: NaN rows) are handed out to the
+// warps of the grid from a device-wide cursor.  The warp computes every neighbour's (bin, weight), sorts
+// the records by key = bin | d2 | index with a bitonic network in its own slice of shared memory, sums
+// every bin's run in that order (PCL's order, bit-identical) and writes the 1980-float row as zeros plus
+// the few non-zero bins.
+constexpr int DW_CAP = 512;     // neighbours per keypoint of the warp kernel
+constexpr int DW_WARPS = 8;
+constexpr size_t desc_warp_smem_bytes() { return (size_t)DW_WARPS * DW_CAP * 12; }
+
+__global__ void __launch_bounds__(DW_WARPS * 32) k_desc_hist_warp(
+    const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
+    int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted,
+    const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
+    const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
+    const unsigned* __restrict__ nbrPool, const int* __restrict__ kpNbrOff, const int* __restrict__ kpRank,
+    float* __restrict__ desc, int descStride, int descOff, DevCounters* __restrict__ ctr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long* key = (unsigned long long*)smem_raw + (size_t)w * DW_CAP;
+  float* wgt = (float*)((unsigned long long*)smem_raw + (size_t)DW_WARPS * DW_CAP) + (size_t)w * DW_CAP;
+  const int total = kpOff[n_scans];
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(&ctr->kw_cursor, 1);
+    g = __shfl_sync(FE_FULL, g, 0);
+    if (g >= total) break;
+    const int nb = kpNbr[g];
+    const int off = kpNbrOff[g];
+    if (nb > DW_CAP || (nb > 0 && off < 0)) continue;  // the block kernels' keypoint
+    float* out = desc + (long long)g * descStride + descOff;
+    const int rank = (nb > 0) ? kpRank[g] : 0;
+    if (nb == 0 || rank >= axesCap) {  // no neighbour (or non-finite keypoint): NaN row (3dsc.hpp)
+      if (nb > 0 && lane == 0) atomicOr(&ctr->err, ERR_AXIS_CAP);
+      for (int i = lane; i < FE_DESC_LEN; i += 32) out[i] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    const int s = kpScan[g];
+    const float4 o = kpOut[g];
+    const long long base = scan_off[s];
+    const float4* so = sorted + base;
+    const int* rh = rho + base;
+    const float2 ax = axes[rank];
+    // records
+    int n = 0;
+    for (int t0 = 0; t0 < nb; t0 += 32) {
+      const int t = t0 + lane;
+      bool has = false;
+      unsigned long long k = 0;
+      float wv = 0.f;
+      if (t < nb) {
+        const int i = (int)nbrPool[off + t];
+        const float4 q = so[i];
+        const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
+        int bin;
+        has = shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wv);
+        k = ((unsigned long long)bin << 52) | ((unsigned long long)__float_as_uint(d2) << 20) |
+            (unsigned long long)((unsigned)__float_as_int(q.w) & 0xFFFFFu);
+      }
+      const unsigned hm = __ballot_sync(FE_FULL, has);
+      if (has) { const int slot = n + __popc(hm & lanemask_lt()); key[slot] = k; wgt[slot] = wv; }
+      n += __popc(hm);
+    }
+    int np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + lane; i < np2; i += 32) { key[i] = ~0ull; wgt[i] = 0.f; }
+    __syncwarp();
+    // bitonic sort of (key, weight), ascending
+    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (np2 >> 1); t += 32) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+          const int l = i | j;
+          const bool up = (i & k2) == 0;
+          const unsigned long long a = key[i], b = key[l];
+          if ((a > b) == up) {
+            key[i] = b; key[l] = a;
+            const float wa = wgt[i]; wgt[i] = wgt[l]; wgt[l] = wa;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // the row: zeros, then every bin's sum in key order
+    {
+      float4* o4 = reinterpret_cast<float4*>(out);  // rows are 16-byte aligned in both layouts? only when descStride/descOff allow
+      if ((((unsigned long long)out) & 15ull) == 0ull) {
+        for (int i = lane; i < FE_DESC_LEN / 4; i += 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int i = lane; i < FE_DESC_LEN; i += 32) out[i] = 0.0f;
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const unsigned bin = (unsigned)(key[i] >> 52);
+      if (i == 0 || (unsigned)(key[i - 1] >> 52) != bin) {
+        float acc = 0.0f;
+        for (int t = i; t < n && (unsigned)(key[t] >> 52) == bin; t++) acc = __fadd_rn(acc, wgt[t]);
+        out[bin] = acc;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -2032,24 +2227,24 @@ __global__ void __launch_bounds__(256) k_boundary_support(
   }
 }
 
-// marked surface points against the surface (slot 3): the sweep of K4c; runs while rho still holds
-// the marks -(scan+1) that K4b left
+// marked surface points against the surface (slot 3): the sweep of K4c over whole cell columns; one block per
+// scan; runs while rho still holds the marks that K4b left
 __global__ void __launch_bounds__(256) k_boundary_density(
-    const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P, long long total,
+    const float4* __restrict__ sorted, SurfIndex X, const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ surfN,
     const int* __restrict__ rho, BoundarySpec B, unsigned long long* __restrict__ bnd) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int v = rho[i];
-    if (v >= 0) continue;
-    const int s = -v - 1;
-    const long long base = scan_off[s];
-    const float4* so = sorted + base;
-    const unsigned* sk = X.sortedKey + base;
-    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
-    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
-    const float4 p = sorted[i];
+  const int s = blockIdx.x;
+  const int n = surfN[s];
+  const long long base = scan_off[s];
+  const float4* so = sorted + base;
+  const unsigned* sk = X.sortedKey + base;
+  const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+  const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+  unsigned long long cnt = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (rho[base + i] >= 0) continue;
+    const float4 p = so[i];
     const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, P.sg_ny);
-    unsigned long long cnt = 0;
     for (int r = cy0; r <= cy1; r++) {
       int b, e;
       row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
@@ -2058,8 +2253,8 @@ __global__ void __launch_bounds__(256) k_boundary_density(
         if (on_boundary(B, 3, l2_simple(p.x, p.y, p.z, q.x, q.y, q.z))) cnt++;
       }
     }
-    if (cnt) atomicAdd(&bnd[4 * s + 3], cnt);
   }
+  if (cnt) atomicAdd(&bnd[4 * s + 3], cnt);
 }
 
 // test hook: the device's fdlibm restatement (glibc_f32.h) element-wise; op 0 atan2f(a,b), 1 acosf(a), 2 atanf(a)

@@ -282,18 +282,11 @@ class FeatureExtractionNode:
         self._check(N.lib().fe_enable_cloud_outputs(self._ctx, 1 if enable else 0))
 
     def cloudOutputs(self, n_scans):
-        """~cloud (src:137-139) and ~keypoint_cloud (src:133-135) of the last single-sub-batch call."""
+        """~cloud (src:137-139) and ~keypoint_cloud (src:133-135) of the last host batch call."""
         co, kco = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
         cp, kcp = C.c_void_p(), C.c_void_p()
         self._check(N.lib().fe_get_cloud_outputs(self._ctx, C.byref(co), C.byref(cp), C.byref(kco), C.byref(kcp)))
-        co = np.ctypeslib.as_array(co, shape=(n_scans + 1,)).copy()
-        kco = np.ctypeslib.as_array(kco, shape=(n_scans + 1,)).copy()
-
-        def arr(p, n):
-            if n == 0 or not p:
-                return np.zeros((0, 4), np.float32)
-            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, 4)).copy()
-        return co, arr(cp, int(co[-1])), kco, arr(kcp, int(kco[-1]))
+        return _unpack_clouds(co, cp, kco, kcp, n_scans)
 
     def setAngleLibm(self, correctly_rounded=False):
         """fe_set_angle_libm: fdlibm atan2f/acosf (glibc <= 2.40, default) or correctly rounded (>= 2.41)."""
@@ -343,7 +336,12 @@ class FeatureExtractionNode:
         self._check(N.lib().fe_get_batch_stats(self._ctx, _ptr(out)))
         keys = ("points", "surface_points", "crop_points", "ring_clusters", "keypoints", "neighbours",
                 "deferred_ring_scans", "deferred_merge_scans", "deferred_surface_scans", "descriptors_unordered")
-        return dict(zip(keys, (int(v) for v in out)))
+        st = dict(zip(keys, (int(v) for v in out)))
+        w = np.zeros(3, np.int64)
+        if N.lib().fe_debug_density_work(self._ctx, _ptr(w)) == N.FE_OK:
+            st["density_tests"], st["marked_points"], st["halo_points"] = (int(v) for v in w)
+            st["density_tests_per_marked_point"] = float(w[0]) / max(int(w[1]), 1)
+        return st
 
     def enableStageTiming(self, enable=True):
         """fe_enable_stage_timing: serialise the stages and time each one (see stageTimes)."""
@@ -355,6 +353,17 @@ class FeatureExtractionNode:
         n = C.c_int32(0)
         self._check(N.lib().fe_get_stage_times(self._ctx, 32, names, ms, C.byref(n)))
         return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+
+def _unpack_clouds(co, cp, kco, kcp, n_scans):
+    co = np.ctypeslib.as_array(co, shape=(n_scans + 1,)).copy()
+    kco = np.ctypeslib.as_array(kco, shape=(n_scans + 1,)).copy()
+
+    def arr(p, n):
+        if n == 0 or not p:
+            return np.zeros((0, 4), np.float32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, 4)).copy()
+    return co, arr(cp, int(co[-1])), kco, arr(kcp, int(kco[-1]))
 
 
 class MultiGpuExtractor:
@@ -379,6 +388,19 @@ class MultiGpuExtractor:
         if st != N.FE_OK:
             raise FeatureExtractionError(st, "fe_multi_enable_record_output")
         self.record_output = bool(enable)
+
+    def enableCloudOutputs(self, enable=True):
+        st = N.lib().fe_multi_enable_cloud_outputs(self._m, 1 if enable else 0)
+        if st != N.FE_OK:
+            raise FeatureExtractionError(st, "fe_multi_enable_cloud_outputs")
+
+    def cloudOutputs(self, n_scans):
+        co, kco = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        cp, kcp = C.c_void_p(), C.c_void_p()
+        st = N.lib().fe_multi_get_cloud_outputs(self._m, C.byref(co), C.byref(cp), C.byref(kco), C.byref(kcp))
+        if st != N.FE_OK:
+            raise FeatureExtractionError(st, (N.lib().fe_multi_last_error(self._m) or b"").decode())
+        return _unpack_clouds(co, cp, kco, kcp, n_scans)
 
     def close(self):
         if self._m:

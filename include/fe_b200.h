@@ -148,12 +148,17 @@ const char* fe_multi_last_error(const fe_multi_t* m);
 /* Copy `bytes` of a device-resident result (fe_process_batch_device) to host memory. */
 int fe_download(fe_ctx_t* ctx, void* host_dst, const void* device_src, int64_t bytes);
 
-/* Optional extra outputs of the last fe_process_batch() of ONE sub-batch (n_scans <=
- * max_scans_per_call): ~keypoint_cloud (src:133-135) and ~cloud (src:137-139), CSR by scan.
- * Enabled with fe_enable_cloud_outputs(ctx, 1) before the call. */
+/* Optional extra outputs of the last fe_process_batch() / fe_process_batch_layout() (any number of
+ * sub-batches): ~keypoint_cloud (src:133-135, the points of every gated ring cluster in the order
+ * src:323 appends them) and ~cloud (src:137-139, the cropped cloud), CSR by scan, gathered on the device
+ * and copied into context-owned pinned memory (valid until the next call).  Enabled with
+ * fe_enable_cloud_outputs(ctx, 1) before the call; fe_multi_* concatenates the shards' outputs. */
 int fe_enable_cloud_outputs(fe_ctx_t* ctx, int32_t enable);
 int fe_get_cloud_outputs(fe_ctx_t* ctx, const int64_t** cloud_offsets, const fe_point_t** cloud,
                          const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud);
+int fe_multi_enable_cloud_outputs(fe_multi_t* m, int32_t enable);
+int fe_multi_get_cloud_outputs(fe_multi_t* m, const int64_t** cloud_offsets, const fe_point_t** cloud,
+                               const int64_t** kpcloud_offsets, const fe_point_t** keypoint_cloud);
 
 /* Record output — pcl::concatenateFields(*keypoints, *descriptors, *pt_descriptors) at src:119 done
  * on the device: when enabled, `descriptors` of every following result (fe_process_batch,

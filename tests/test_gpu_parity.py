@@ -299,3 +299,33 @@ def test_run_based_and_grid_based_ring_clustering_agree(ob, synth, nodes, cfg, n
     ko_o, kp_o, _, _ = ob.process_batch(P, sh, offs[: n2 + 1], rp[:n2], mode=1, n_threads=8, want_desc=False)
     ko, kp, d = nd.processBatch(sh, offs[: n2 + 1], rp[:n2])
     assert np.array_equal(ko, ko_o) and bits_equal(kp, kp_o)
+
+
+def test_cloud_outputs_across_sub_batches_and_shards(ob, synth):
+    """~cloud (src:137-139) and ~keypoint_cloud (src:133-135) of a call that the library cuts into several
+    sub-batches (two slots, device-side gather into pinned memory), and of the in-process multi-GPU form,
+    equal the oracle's per-scan clouds bit for bit."""
+    from feature_extraction_b200 import FeatureExtractionNode, MultiGpuExtractor
+    P = ob.node_default()
+    pts, offs, rp = synth.generate(2, 37, scan_index_base=9100)
+    pts = pts.copy()
+    pts[offs[11]:offs[12], 0] -= 500.0    # a scan that is cropped away entirely, in the middle
+    want = [ob.process_scan(P, pts[offs[s]:offs[s + 1]], rp[s, 0], rp[s, 1], mode=1) for s in range(37)]
+    nd = FeatureExtractionNode(to_fe_params(P), max_points=1 << 20, max_scans=8, max_keypoints=4096)   # 5 sub-batches
+    nd.enableCloudOutputs(True)
+    for rep in range(2):                  # the second call reuses (and may regrow) the pinned result buffers
+        ko, kp, d = nd.processBatch(pts, offs, rp)
+        co, cloud, kco, kcloud = nd.cloudOutputs(37)
+        for s in range(37):
+            assert bits_equal(cloud[co[s]:co[s + 1]], want[s]["cloud"]), s
+            assert bits_equal(kcloud[kco[s]:kco[s + 1]], want[s]["keypoint_cloud"]), s
+            assert bits_equal(kp[ko[s]:ko[s + 1]], want[s]["keypoints"]), s
+    nd.close()
+    m = MultiGpuExtractor([0, 0, 0], to_fe_params(P), max_points=1 << 20, max_scans=5, max_keypoints=4096)
+    m.enableCloudOutputs(True)
+    ko, kp, d = m.processBatch(pts, offs, rp)
+    co, cloud, kco, kcloud = m.cloudOutputs(37)
+    m.close()
+    for s in range(37):
+        assert bits_equal(cloud[co[s]:co[s + 1]], want[s]["cloud"]), s
+        assert bits_equal(kcloud[kco[s]:kco[s + 1]], want[s]["keypoint_cloud"]), s

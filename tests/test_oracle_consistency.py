@@ -169,3 +169,36 @@ def test_boundary_report_is_the_same_from_both_search_back_ends(ob, synth):
         for mode in (0, 1):
             r = ob.process_batch_boundary(P, sc, np.array([0, len(sc)], np.int64), np.zeros((1, 2)), 1e-6, mode=mode)
             assert (r[0, 0] >= 1) == expect, (gap, mode, r)
+
+
+def test_oracle_exports_the_product_symbols(ob, synth):
+    """the oracle's shared object exports the same create / process / destroy / last_error /
+    version symbols as the product library, with the same structs — a harness written against
+    include/fe_b200.h can be pointed at either .so."""
+    import ctypes as C
+    import os
+    from feature_extraction_b200 import _native as N   # struct definitions only; the product .so is not called here
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L = C.CDLL(os.path.join(root, "oracle", "libfe_oracle.so"))
+    L.fe_version.restype = C.c_char_p
+    L.fe_last_error.restype = C.c_char_p
+    L.fe_create.argtypes = [C.c_int, C.POINTER(N.Params), C.POINTER(N.Limits), C.POINTER(C.c_void_p)]
+    L.fe_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(N.BatchResult)]
+    L.fe_destroy.argtypes = [C.c_void_p]
+    assert b"oracle" in L.fe_version() and L.fe_device_count() == 0
+    P = N.Params()
+    L.fe_params_node_default(C.byref(P))
+    ctx = C.c_void_p()
+    assert L.fe_create(0, C.byref(P), None, C.byref(ctx)) == 0
+    pts, offs, rp = synth.generate(2, 4, scan_index_base=31)
+    rpf = np.ascontiguousarray(rp, np.float64).reshape(-1)
+    res = N.BatchResult()
+    assert L.fe_process_batch(ctx, pts.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), rpf.ctypes.data_as(C.c_void_p), 4, C.byref(res)) == 0
+    K = int(res.n_keypoints)
+    ko = np.ctypeslib.as_array(res.keypoint_offsets, shape=(5,)).copy()
+    kp = np.ctypeslib.as_array(C.cast(res.keypoints, C.POINTER(C.c_float)), shape=(K, 4)).copy()
+    d = np.ctypeslib.as_array(C.cast(res.descriptors, C.POINTER(C.c_float)), shape=(K, 1980)).copy()
+    L.fe_destroy(ctx)
+    ko_o, kp_o, d_o, _ = ob.process_batch(ob.node_default(), pts, offs, rp, mode=1)
+    assert np.array_equal(ko, ko_o) and np.array_equal(kp.view(np.uint32), kp_o.view(np.uint32))
+    assert np.array_equal(d.view(np.uint32), d_o.view(np.uint32))

@@ -14,7 +14,7 @@ import shutil
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STAGE_OF = [("k_level_crop_ring", "K1 level+crop+ring"), ("k_cluster_rings", "K2 ring clusters"),
+STAGE_OF = [("k_level_crop_ring", "K1 level+crop+ring"), ("k_ring_runs", "K2 ring clusters"), ("k_cluster_rings", "K2 ring clusters"),
             ("k_merge_keypoints", "K3 merge keypoints"), ("k_kp_rank", "K4b mark neighbours"), ("k_kp_", "keypoint CSR"),
             ("k_surface_grid", "K4a surface grid"), ("k_desc_mark", "K4b mark neighbours"),
             ("k_density", "K4c density"), ("k_desc_hist", "K4d shape context")]
@@ -43,7 +43,7 @@ def read_launches(path):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r1_final"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r2_final"
     src = os.path.join(ROOT, "gpurun_out", tag)
     dst = os.path.join(ROOT, "profiles")
     for name in ("bench_config1", "bench_config2", "bench_config3", "bench_config4", "bench_reference_arm"):
@@ -103,7 +103,7 @@ def main():
         return x * scale
 
     md = ["# %s — `ncu --set full --clock-control none` extracts, config 2, 1000 scans per launch" % tag, "",
-          "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_cluster_rings|k_level_crop|k_surface_grid_cells|"
+          "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_ring_runs|k_level_crop|k_surface_grid_cells|"
           "k_density|k_desc_hist|k_desc_mark|k_merge\" -c 14 -o ... python bench.py --scans 1000 --steps 1 --warmup 0 --no-cpu-baseline` "
           "(raw page: `%s_ncu_full_raw_1000scans.csv`; script `tools/final_profile.sh`).  Cold caches, serialised launches." % tag, "",
           "| kernel | time µs | DRAM read MB | DRAM write MB | regs | grid×block | warps active % | DRAM % | issue active % | thr/inst | L2 hit % |",
