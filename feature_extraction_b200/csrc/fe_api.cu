@@ -502,9 +502,11 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, c
   ctx->launches += 2;
 }
 
-void launch_density(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P) {
+void launch_density(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int64_t npts) {
   if (nscans <= 0) return;
-  k_density<<<nscans, 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, s.d_surfN, s.d_rho, s.d_ctr->dens_work);
+  // blocks per scan: about one per 8k points of an average scan (a dense scan's halo is tens of tiles)
+  const int by = (int)std::max<int64_t>(1, std::min<int64_t>(16, npts / std::max(nscans, 1) / 8192 + 1));
+  k_density<<<dim3((unsigned)nscans, (unsigned)by), 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, s.d_surfN, s.d_rho, s.d_ctr->dens_work);
   ctx->launches++;
 }
 
@@ -654,7 +656,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
                                                          boundary_spec(ctx), s.d_bnd);
       ctx->launches += 2;
     }
-    launch_density(ctx, s, nscans, P);
+    launch_density(ctx, s, nscans, P, npts);
     mark(ctx, s, "K4c density");
     launch_desc_hist(ctx, s, nscans, P, gridKp, ctx->recordOutput);
     mark(ctx, s, "K4d shape context");
@@ -1438,7 +1440,7 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
     return restore(fail(ctx, FE_ERR_CUDA, "staging of the descriptor inputs failed"));
   launch_surface_grid(ctx, s, 1, P, s.stream);
   launch_desc_mark(ctx, s, 1, P, 148 * 4);
-  launch_density(ctx, s, 1, P);
+  launch_density(ctx, s, 1, P, n);
   launch_desc_hist(ctx, s, 1, P, 148 * 4, false);
   ctx->dp = saved;
   CK(cudaGetLastError());

@@ -1605,7 +1605,7 @@ __global__ void __launch_bounds__(256) k_kp_rank(const int* __restrict__ kpScan,
 // K4c — local point density (3dsc.hpp: searchForNeighbors(point_density_radius_)), once per
 // marked surface point instead of once per (keypoint, neighbour) as PCL does.
 // ============================================================================================
-// One block per scan walks the scan's sorted (halo) points in tiles: the marked ones of a tile are
+// Blocks (scan, y) walk the scan's sorted (halo) points in tiles: the marked ones of a tile are
 // compacted into a list (they stay in cell order, so neighbouring lanes share cells and their loads hit
 // L1), then every thread takes one marked point and sweeps the three rows of cells its density sphere
 // touches (contiguous spans, fixed trip counts).
@@ -1626,7 +1626,8 @@ __global__ void __launch_bounds__(256) k_density(
   const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
   const int nx = P.sg_nx, ny = P.sg_ny;
   unsigned ntest = 0, nmark = 0;  // per thread: at most 65,535 candidates per marked point, a few marked points
-  for (int t0 = 0; t0 < n; t0 += DENS_TILE) {
+  // blockIdx.y strides over the scan's tiles: dense scans are shared by several blocks
+  for (int t0 = (int)blockIdx.y * DENS_TILE; t0 < n; t0 += (int)gridDim.y * DENS_TILE) {
     // marked points of the tile, in order
     int cntw = 0;
     unsigned mk[DENS_TILE / 256];
@@ -1927,26 +1928,37 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
         wB[pos] = wA[i];
       }
       __syncthreads();
-      // (3) rank every record inside its bin: position = bin start + number of smaller keys
+      // (3) rank every record inside its bin: position = bin start + number of smaller keys.  After (2) binCnt[b]
+      //     is the END of bin b, so a bin's segment is [binCnt[b-1], binCnt[b]): fixed trip counts, no key decoding
       for (int i = tid; i < n; i += NT) {
         const unsigned long long k = keyB[i];
-        const unsigned bin = (unsigned)(k >> 52);
-        int smaller = 0, left = 0;
-        for (int t = i - 1; t >= 0 && (unsigned)(keyB[t] >> 52) == bin; t--) { left++; smaller += (keyB[t] < k) ? 1 : 0; }
-        for (int t = i + 1; t < n && (unsigned)(keyB[t] >> 52) == bin; t++) smaller += (keyB[t] < k) ? 1 : 0;
-        const int pos = i - left + smaller;
-        keyA[pos] = k;
-        wA[pos] = wB[i];
+        const int bin = (int)(k >> 52);
+        const int b0 = bin ? binCnt[bin - 1] : 0, e0 = binCnt[bin];
+        int smaller = 0;
+        for (int t = b0; t < e0; t++) smaller += (keyB[t] < k) ? 1 : 0;
+        keyA[b0 + smaller] = k;
+        wA[b0 + smaller] = wB[i];
       }
-      for (int i = tid; i < FE_DESC_LEN; i += NT) hist[i] = 0.0f;  // the counters are no longer needed
-      __syncthreads();
-      // (4) sum every bin in order
-      for (int i = tid; i < n; i += NT) {
-        const unsigned bin = (unsigned)(keyA[i] >> 52);
-        if (i == 0 || (unsigned)(keyA[i - 1] >> 52) != bin) {
-          float acc = 0.0f;
-          for (int t = i; t < n && (unsigned)(keyA[t] >> 52) == bin; t++) acc = __fadd_rn(acc, wA[t]);
-          hist[bin] = acc;
+      // (4) sum every bin in order: a thread owns PER consecutive bins; their bounds are read before the sums
+      //     overwrite the counters (hist shares their storage)
+      {
+        constexpr int PER = (FE_DESC_LEN + NT - 1) / NT;
+        int bnd[PER + 1];
+        bnd[0] = (tid * PER > 0 && tid * PER <= FE_DESC_LEN) ? binCnt[tid * PER - 1] : 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+          const int bi = tid * PER + k;
+          bnd[k + 1] = (bi < FE_DESC_LEN) ? binCnt[bi] : n;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+          const int bi = tid * PER + k;
+          if (bi < FE_DESC_LEN) {
+            float acc = 0.0f;
+            for (int t = bnd[k]; t < bnd[k + 1]; t++) acc = __fadd_rn(acc, wA[t]);
+            hist[bi] = acc;
+          }
         }
       }
       __syncthreads();
