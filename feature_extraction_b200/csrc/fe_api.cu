@@ -41,9 +41,9 @@ struct Slot {
   int *d_perScan2 = nullptr, *d_outOff2 = nullptr;   // cloud outputs: ~keypoint_cloud counts / offsets
   float4* d_gather2 = nullptr;
   int *h_cloudOff = nullptr, *h_kcOff = nullptr;     // pinned: per-scan offsets of the two cloud outputs of the sub-batch
-  unsigned short* d_cellTab = nullptr;
+  unsigned char* d_gridHdr = nullptr;  // per-scan index of the halo cell grid (bit map, word prefix, slot table)
   int* d_tabOk = nullptr;
-  int64_t capCellTab = 0;
+  int64_t capGridHdr = 0;
   int *d_ovfRings = nullptr, *d_ovfRings2 = nullptr, *d_ovfMerge = nullptr, *d_ovfMerge2 = nullptr, *d_ovfSurf = nullptr;
   unsigned char* d_slabs = nullptr;
   int64_t capRowStart = 0;
@@ -201,6 +201,8 @@ void surface_grid(DevParams& dp, double R, float x0, float x1, float y0, float y
   dp.Rpad = (float)(R * 1.0001 + 1e-6);
   dp.rhopad = (float)(rrho * 1.0001 + 1e-6);
   dp.halopad = (float)((R + rrho) * 1.0002 + 4e-6);
+  dp.zs0 = z0 - (float)(2.0 * rrho);  // z slabs of the cell grid: uniform over the keypoints' z range grown by 2 R/5, clamped outside
+  dp.zs_inv_range = 1.0f / std::max((z1 + (float)(2.0 * rrho)) - dp.zs0, 1e-3f);
 }
 
 int derive_params(fe_ctx* ctx, const fe_params_t& p) {
@@ -243,7 +245,7 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_ringPts, s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_cellTab, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_perScan2, s.d_outOff2, s.d_gather2};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_gridHdr, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_perScan2, s.d_outOff2, s.d_gather2};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
   for (void* p : hv) if (p) cudaFreeHost(p);
@@ -366,11 +368,11 @@ int ensure_rowstart(fe_ctx* ctx, Slot& s, int nscans) {
   }
   const int64_t ncells = (int64_t)ctx->dp.sg_nx * ctx->dp.sg_ny;
   if (ncells <= SURF_MAX_CELLS) {
-    const int64_t needT = (int64_t)std::max(nscans, s.capScans) * ((ncells + 2) & ~1LL);
-    if (needT > s.capCellTab) {
-      if (s.d_cellTab) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.d_cellTab)); s.d_cellTab = nullptr; }
-      CK(dalloc(&s.d_cellTab, (size_t)needT));
-      s.capCellTab = needT;
+    const int64_t needT = (int64_t)std::max(nscans, s.capScans) * grid_hdr_bytes((int)ncells);
+    if (needT > s.capGridHdr) {
+      if (s.d_gridHdr) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.d_gridHdr)); s.d_gridHdr = nullptr; }
+      CK(dalloc(&s.d_gridHdr, (size_t)needT));
+      s.capGridHdr = needT;
     }
   }
   return FE_OK;
@@ -381,9 +383,9 @@ SurfIndex surf_index(const fe_ctx* ctx, const Slot& s) {
   SurfIndex X;
   X.sortedKey = s.d_sortedKey;
   X.rowStart = s.d_rowStart;
-  X.cellTab = (ncells <= SURF_MAX_CELLS) ? s.d_cellTab : nullptr;
+  X.gridHdr = (ncells <= SURF_MAX_CELLS) ? s.d_gridHdr : nullptr;
+  X.gridStride = grid_hdr_bytes((int)ncells);
   X.tabOk = s.d_tabOk;
-  X.ncells1 = (int)((ncells + 2) & ~1LL);
   return X;
 }
 
@@ -488,8 +490,8 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, c
   const int ncells = P.sg_nx * P.sg_ny;
   if (ncells <= SURF_MAX_CELLS) {
     k_surface_grid_cells<NT_SURF><<<nscans, NT_SURF, surf_cells_smem_bytes(ncells), q>>>(
-        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_kpOut, s.d_kpOff, s.d_sorted, s.d_rho, s.d_rowStart,
-        s.d_surfN, s.d_ctr, s.d_ovfSurf, s.d_cellTab, s.d_tabOk);
+        s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_kpOut, s.d_kpOff, s.d_sorted, s.d_rho,
+        s.d_surfN, s.d_ctr, s.d_ovfSurf, s.d_gridHdr, grid_hdr_bytes(ncells), s.d_tabOk);
     k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
                                                                    s.d_keyB, s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey,
                                                                    s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf,

@@ -75,6 +75,7 @@ struct DevParams {
   // 3DSC
   float R2f, rho2f, Rpad, rhopad;
   float halopad;  // R + R/5 padded: only surface points this close (in x and in y) to a keypoint can matter
+  float zs0, zs_inv_range;  // z slabs of the cell grid: slab = clamp(floor((z - zs0) * NS * zs_inv_range), 0, NS-1)
   float radii[16], theta[12], phi[13];
   int estimate_descriptors;
   int angle_libm;  // 0: fdlibm atan2f/acosf (glibc <= 2.40), 1: correctly rounded (glibc >= 2.41)
@@ -1323,44 +1324,59 @@ __global__ void __launch_bounds__(NT2, 2) k_surface_grid(
 // Scans with more than 65,535 surface points (16-bit counters) are deferred to the radix kernel.
 constexpr int NT_SURF = 512;           // threads of the counting-sort K4a (384 was measured: slower)
 constexpr int SURF_MAX_CELLS = 57344;  // 112 KB of counters: 2 blocks / SM at the upper end
-constexpr size_t surf_cells_smem_bytes(int ncells) {
-  return (size_t)((((ncells + 1) / 2) + 3) & ~3) * 4 + 64 + (size_t)((ncells + 31) / 32) * 4 + 16;  // counters + halo bit map
-}
 
 // The cell grid only ever serves the 3DSC stage, and that only looks at surface points within R of a
 // keypoint (support) or within R + R/5 (density of the support points).  The kernel therefore runs after
 // the keypoints are known and keeps only the points of HALO cells — cells a keypoint's box of half-width
 // R + R/5 touches (a bit map in shared memory) — which is a few percent of a sparse scan.  Scans without
-// keypoints are not read at all.  (Ordering every cell by z so that the density sweep could binary-search
-// its z window was built and measured: 2x fewer distance tests, but the searches and the data-dependent
-// loop ends cost more than the tests they saved — K4c 0.90 -> 1.02 ms on config 2, 15.7 -> 33.9 ms on
-// config 3 — so the order inside a cell stays free.)
+// keypoints are not read at all.  Halo cells are numbered in cell order (rank = bits set before the cell:
+// a per-word prefix plus a popcount), and every halo cell is cut into NS z slabs: the counting sort runs
+// over (rank, slab), so that a cell's points are grouped by slab and the density sweep (K4c) visits only
+// the slabs its z window touches, while a row of cells over all slabs is still one contiguous span for
+// the support sweeps (K4b, K4d).  NS = min(16, GRID_TAB_CAP / halo cells) per scan.
+// Per-scan index in global memory (GridHdr): bit map | word prefix | NS, halo cells | slot table.
+constexpr int GRID_TAB_CAP = 28672;     // (halo cell, slab) counters per scan: 56 KB of 16-bit counters in shared memory
+constexpr int GRID_MAX_SLABS = 16;
+constexpr int GRID_SLAB_MIN_POINTS = 20000;  // surface points of a scan from which its cells are cut into z slabs
+__host__ __device__ constexpr long long grid_hdr_bytes(int ncells) {
+  // bitmap words, word prefix (u16, one extra, padded to 4 B), 2 meta words, table (u16, TAB_CAP + 2)
+  return (long long)((ncells + 31) / 32) * 4 + (long long)((((ncells + 31) / 32) + 2) / 2) * 4 + 8 + (long long)(GRID_TAB_CAP + 2) * 2;
+}
+constexpr size_t surf_cells_smem_bytes(int ncells) {
+  return (size_t)((GRID_TAB_CAP + 2) / 2) * 4 + 64 + (size_t)((ncells + 31) / 32) * 4 + 16 + (size_t)((ncells + 31) / 32 + 2) * 2 + 16;
+}
+
+__device__ __forceinline__ int z_slab(float z, float zs0, float zs_scale, int ns) {
+  const int l = (int)floorf((z - zs0) * zs_scale);
+  return max(0, min(l, ns - 1));
+}
+
 template <int NTS>
 __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     const float4* __restrict__ surf, const int* __restrict__ surfCnt,
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P,
     const float4* __restrict__ kpOut, const int* __restrict__ kpOff,
-    float4* __restrict__ sorted, int* __restrict__ rho, int* __restrict__ rowStart,
+    float4* __restrict__ sorted, int* __restrict__ rho,
     int* __restrict__ surfN, DevCounters* __restrict__ ctr, int* __restrict__ ovfList,
-    unsigned short* __restrict__ cellTab, int* __restrict__ tabOk) {
+    unsigned char* __restrict__ gridHdr, long long gridStride, int* __restrict__ tabOk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nx = P.sg_nx, ny = P.sg_ny, ncells = nx * ny, nwords = (ncells + 1) / 2, nbm = (ncells + 31) / 32;
-  unsigned* cells = (unsigned*)smem_raw;        // packed pairs of 16-bit counters / cursors
-  unsigned* halo = cells + ((nwords + 3) & ~3) + 16;  // one bit per cell
+  const int nx = P.sg_nx, ny = P.sg_ny, ncells = nx * ny, nbm = (ncells + 31) / 32;
+  unsigned* cnts = (unsigned*)smem_raw;                   // packed pairs of 16-bit counters / cursors over (rank, slab)
+  unsigned* halo = cnts + ((GRID_TAB_CAP + 2) / 2) + 16;  // one bit per cell
+  unsigned short* wpre = (unsigned short*)(halo + nbm + 4);  // halo cells before every bit-map word
   __shared__ int sc[40];
-  __shared__ int s_n;
+  __shared__ int s_n, s_hc;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   constexpr int NW = NTS / 32;
   const long long base = scan_off[s];
   const int c0 = chunk_off[s];
   const int nch = chunk_off[s + 1] - c0;
-  int* rs = rowStart + (long long)s * (ny + 1);
   const int k0 = kpOff[s], k1 = kpOff[s + 1];
   if (k1 == k0) {  // no keypoint: nothing of this scan's surface is ever looked at
     if (tid == 0) { surfN[s] = 0; tabOk[s] = 1; }
     return;
   }
-  // total surface points of the scan (the 16-bit counters hold at most 65,535 of them)
+  // total surface points of the scan (the 16-bit slots hold at most 65,535 of them)
   {
     int v = 0;
     for (int c = tid; c < nch; c += NTS) v += surfCnt[c0 + c];
@@ -1368,7 +1384,6 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     block_excl_scan<NTS>(v, &tot, sc);
     if (tid == 0) s_n = tot;
   }
-  for (int i = tid; i < (nwords + 3) / 4; i += NTS) ((uint4*)cells)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < nbm; i += NTS) halo[i] = 0u;
   __syncthreads();
   if (s_n > 65535) {
@@ -1388,40 +1403,71 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     }
   }
   __syncthreads();
-  const int tabStride = (ncells + 2) & ~1;  // even: every scan's table is 4-byte aligned
-  unsigned short* tab = cellTab + (long long)s * tabStride;
-  // (1) count: the survivors of a chunk are contiguous; the chunks are cut into runs of 256 points that
-  //     are dealt to the warps, eight loads in flight per lane (only x and y are needed here)
-  for (int it = w; it < nch * (CH / 256); it += NW) {
-    const int c = it / (CH / 256);
+  // (1) rank of every halo cell: exclusive prefix of the words' popcounts
+  {
+    int run = 0;
+    for (int w0 = 0; w0 < nbm; w0 += NTS) {
+      const int i = w0 + tid;
+      const int v = (i < nbm) ? __popc(halo[i]) : 0;
+      int tot;
+      const int pos = block_excl_scan<NTS>(v, &tot, sc);
+      if (i < nbm) wpre[i] = (unsigned short)(run + pos);
+      run += tot;
+    }
+    if (tid == 0) { wpre[nbm] = (unsigned short)run; s_hc = run; }
+  }
+  __syncthreads();
+  const int hc = s_hc;
+  // z slabs pay when cell columns are long, i.e. for dense sensors (measured: 4x azimuth density, K4c 13.9 ->
+  // 11.3 ms; at the VLP-16's own density the per-cell lookups cost what the skipped tests save)
+  const int NS = (s_n >= GRID_SLAB_MIN_POINTS) ? max(1, min(GRID_MAX_SLABS, GRID_TAB_CAP / max(hc, 1))) : 1;
+  if (hc > GRID_TAB_CAP) {  // more halo cells than counters: the radix kernel takes the scan
+    if (tid == 0) { ovfList[atomicAdd(&ctr->ovf_surf, 1)] = s; tabOk[s] = 0; }
+    return;
+  }
+  const int nslots = hc * NS, nwords = (nslots + 2) / 2;
+  const float zscale = (float)NS * P.zs_inv_range;
+  for (int i = tid; i < nwords; i += NTS) cnts[i] = 0u;
+  __syncthreads();
+  auto slot_of = [&](float x, float y, float z) -> int {  // (rank, slab) counter of a point, -1 outside the halo
+    const int cell = surf_cell(y, P.sy0, P.sg_inv, ny) * nx + surf_cell(x, P.sx0, P.sg_inv, nx);
+    const unsigned bits = halo[cell >> 5];
+    if (!((bits >> (cell & 31)) & 1u)) return -1;
+    const int rk = (int)wpre[cell >> 5] + __popc(bits & ((1u << (cell & 31)) - 1u));
+    return rk * NS + z_slab(z, P.zs0, zscale, NS);
+  };
+  // (2) count: the survivors of a chunk are contiguous; the chunks are cut into runs of 128 points that
+  //     are dealt to the warps, four 16-byte loads in flight per lane
+  for (int it = w; it < nch * (CH / 128); it += NW) {
+    const int c = it / (CH / 128);
     const int j1 = surfCnt[c0 + c];
     const float4* src = surf + base + (long long)c * CH;
-    const int j = (it % (CH / 256)) * 256 + lane;
+    const int j = (it % (CH / 128)) * 128 + lane;
     if (j - lane >= j1) continue;
-    float2 q[8];
+    float4 q[4];
 #pragma unroll
-    for (int k = 0; k < 8; k++) q[k] = (j + 32 * k < j1) ? *(const float2*)(src + j + 32 * k) : make_float2(0.f, 0.f);
+    for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 4; k++) {
       if (j + 32 * k < j1) {
-        const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
-        if ((halo[cell >> 5] >> (cell & 31)) & 1u) atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
+        const int sl = slot_of(q[k].x, q[k].y, q[k].z);
+        if (sl >= 0) atomicAdd(&cnts[sl >> 1], (sl & 1) ? 65536u : 1u);
       }
     }
   }
   __syncthreads();
-  // (2) exclusive scan over the cells in key order; every thread owns a run of whole words
+  // (3) exclusive scan over the (rank, slab) counters in key order; every thread owns a run of whole words
   {
     const int per = (nwords + NTS - 1) / NTS;
     const int wb = min(tid * per, nwords), we = min(wb + per, nwords);
     int sum = 0;
-    for (int i = wb; i < we; i++) { const unsigned v = cells[i]; sum += (int)(v & 0xFFFFu) + (int)(v >> 16); }
+    for (int i = wb; i < we; i++) { const unsigned v = cnts[i]; sum += (int)(v & 0xFFFFu) + (int)(v >> 16); }
     int tot;
     int run = block_excl_scan<NTS>(sum, &tot, sc);
     for (int i = wb; i < we; i++) {
-      const unsigned v = cells[i];
+      const unsigned v = cnts[i];
       const int lo = (int)(v & 0xFFFFu), hi = (int)(v >> 16);
-      cells[i] = (unsigned)run | ((unsigned)(run + lo) << 16);  // starts of the two cells
+      cnts[i] = (unsigned)run | ((unsigned)(run + lo) << 16);  // starts of the two slots
       run += lo + hi;
     }
     if (tid == 0) s_n = tot;  // halo points only
@@ -1429,23 +1475,26 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
   __syncthreads();
   const int n = s_n;
   if (tid == 0) { surfN[s] = n; tabOk[s] = 1; }
-  for (int r = tid; r <= ny; r += NTS) {
-    int v = n;
-    if (r < ny) { const int cell = r * nx; const unsigned wv = cells[cell >> 1]; v = (cell & 1) ? (int)(wv >> 16) : (int)(wv & 0xFFFFu); }
-    rs[r] = v;
-  }
-  // the table of cell starts for K4b-d: exactly the packed words (low half = even cell).  With an odd
-  // cell count the spare high half already holds n (the start of the cell after the last one).
+  // the scan's index for K4b-d: bit map, word prefix, NS / halo cells, and the table of slot starts — exactly
+  // the packed words (low half = even slot; entry nslots, the end of the last slot, is n by construction
+  // because the unused tail counters are zero)
   {
-    unsigned* tabw = (unsigned*)tab;
-    for (int i = tid; i < nwords; i += NTS) tabw[i] = cells[i];
-    if (tid == 0 && (ncells & 1) == 0) tabw[nwords] = (unsigned)n;
+    unsigned* g = (unsigned*)(gridHdr + (long long)s * gridStride);
+    for (int i = tid; i < nbm; i += NTS) g[i] = halo[i];
+    unsigned* gp = g + nbm;
+    const unsigned* wp32 = (const unsigned*)wpre;
+    const int npw = (nbm + 2) / 2;
+    for (int i = tid; i < npw; i += NTS) gp[i] = wp32[i];
+    unsigned* gm = gp + npw;
+    if (tid == 0) { gm[0] = (unsigned)NS; gm[1] = (unsigned)hc; }
+    unsigned* gt = gm + 2;
+    for (int i = tid; i < nwords; i += NTS) gt[i] = cnts[i];
   }
   for (int i = tid; i < n; i += NTS) rho[base + i] = 0;  // K4b marks, K4c counts: only these slots are ever used
   __syncthreads();
   if (n == 0) return;
-  // (3) scatter: the start of a cell doubles as its cursor (it ends at the cell's end <= n <= 65535, so a
-  //     16-bit half never carries into its neighbour); the order inside a cell is free
+  // (4) scatter: the start of a slot doubles as its cursor (it ends at the slot's end <= n <= 65535, so a
+  //     16-bit half never carries into its neighbour); the order inside a slot is free
   float4* so = sorted + base;
   for (int it = w; it < nch * (CH / 128); it += NW) {
     const int c = it / (CH / 128);
@@ -1459,44 +1508,86 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       if (j + 32 * k < j1) {
-        const int cell = surf_cell(q[k].y, P.sy0, P.sg_inv, ny) * nx + surf_cell(q[k].x, P.sx0, P.sg_inv, nx);
-        if ((halo[cell >> 5] >> (cell & 31)) & 1u) {
-          const unsigned old = atomicAdd(&cells[cell >> 1], (cell & 1) ? 65536u : 1u);
-          so[(cell & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu)] = q[k];
+        const int sl = slot_of(q[k].x, q[k].y, q[k].z);
+        if (sl >= 0) {
+          const unsigned old = atomicAdd(&cnts[sl >> 1], (sl & 1) ? 65536u : 1u);
+          so[(sl & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu)] = q[k];
         }
       }
     }
   }
 }
 
-// How K4b-d find the sorted positions of a cell range: through the per-scan table of cell starts that
-// the counting-sort K4a publishes (two loads), or — for scans that went through the radix kernel —
-// by binary search in the sorted keys inside the row.
+// How K4b-d find the sorted positions of a cell range: through the per-scan index that the counting-sort
+// K4a publishes (bit map of halo cells, word prefix -> rank of a cell, table of (rank, slab) slot starts),
+// or — for scans that went through the radix kernel — by binary search in the sorted keys inside the row.
 struct SurfIndex {
-  const unsigned* sortedKey;      // keys of the sorted points (CSR by scan)
-  const int* rowStart;            // [scan][ny+1]
-  const unsigned short* cellTab;  // [scan][stride >= ncells+1, even] first slot of every cell (then n), may be null
-  const int* tabOk;               // [scan] 1: the scan has a cell table
-  int ncells1;                    // the per-scan stride of cellTab in entries
+  const unsigned* sortedKey;      // keys of the sorted points (CSR by scan); radix path only
+  const int* rowStart;            // [scan][ny+1]; radix path only
+  const unsigned char* gridHdr;   // [scan] GridHdr blobs, may be null (grid too large for the counting sort)
+  long long gridStride;
+  const int* tabOk;               // [scan] 1: the scan has a GridHdr
 };
 
-// span of sorted positions of row r whose cell x is in [cx0, cx1]
-__device__ __forceinline__ void row_span(const unsigned* __restrict__ sk, const int* __restrict__ rs,
-                                         const unsigned short* __restrict__ ct, int nx, int r, int cx0, int cx1,
-                                         int bx, int& b, int& e) {
-  if (ct) {
-    b = (int)ct[r * nx + cx0];
-    e = (int)ct[r * nx + cx1 + 1];
-    return;
+struct ScanGrid {                 // one scan's view of the index
+  const unsigned* bm;             // halo bit map; null: radix path
+  const unsigned short* wpre;
+  const unsigned short* tab;
+  int ns, hc, ncells;
+  const unsigned* sk;
+  const int* rs;
+  int nx, bx;
+  float zs0, zscale;
+  __device__ __forceinline__ int rank_lb(int cell) const {  // halo cells with a smaller index
+    if (cell >= ncells) return hc;
+    const unsigned bits = bm[cell >> 5];
+    return (int)wpre[cell >> 5] + __popc(bits & ((1u << (cell & 31)) - 1u));
   }
-  const int rb = rs[r], re = rs[r + 1];
-  const unsigned klo = ((unsigned)r << bx) | (unsigned)cx0, khi = ((unsigned)r << bx) | (unsigned)cx1;
-  int lo = rb, hi = re;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] < klo) lo = mid + 1; else hi = mid; }
-  b = lo;
-  hi = re;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] <= khi) lo = mid + 1; else hi = mid; }
-  e = lo;
+  // span of sorted positions of row r whose cell x is in [cx0, cx1], all slabs
+  __device__ __forceinline__ void row_span(int r, int cx0, int cx1, int& b, int& e) const {
+    if (bm) {
+      b = (int)tab[rank_lb(r * nx + cx0) * ns];
+      e = (int)tab[rank_lb(r * nx + cx1 + 1) * ns];  // cx1 + 1 may be the first cell of the next row: still "cells before it"
+      return;
+    }
+    const int rb = rs[r], re = rs[r + 1];
+    const unsigned klo = ((unsigned)r << bx) | (unsigned)cx0, khi = ((unsigned)r << bx) | (unsigned)cx1;
+    int lo = rb, hi = re;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] < klo) lo = mid + 1; else hi = mid; }
+    b = lo;
+    hi = re;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] <= khi) lo = mid + 1; else hi = mid; }
+    e = lo;
+  }
+  // span of one cell restricted to the slabs that [zlo, zhi] touches (index path only)
+  __device__ __forceinline__ void cell_slab_span(int cell, float zlo, float zhi, int& b, int& e) const {
+    const unsigned bits = bm[cell >> 5];
+    if (!((bits >> (cell & 31)) & 1u)) { b = e = 0; return; }
+    const int rk = (int)wpre[cell >> 5] + __popc(bits & ((1u << (cell & 31)) - 1u));
+    b = (int)tab[rk * ns + z_slab(zlo, zs0, zscale, ns)];
+    e = (int)tab[rk * ns + z_slab(zhi, zs0, zscale, ns) + 1];
+  }
+};
+
+__device__ __forceinline__ ScanGrid scan_grid(const SurfIndex& X, int s, long long base, const DevParams& P) {
+  ScanGrid G;
+  G.sk = X.sortedKey + base;
+  G.rs = X.rowStart + (long long)s * (P.sg_ny + 1);
+  G.nx = P.sg_nx; G.bx = P.sg_bx;
+  G.bm = nullptr; G.wpre = nullptr; G.tab = nullptr; G.ns = 1; G.hc = 0; G.ncells = P.sg_nx * P.sg_ny;
+  G.zs0 = P.zs0; G.zscale = P.zs_inv_range;
+  if (X.gridHdr && X.tabOk[s]) {
+    const int nbm = (P.sg_nx * P.sg_ny + 31) / 32;
+    const unsigned* g = (const unsigned*)(X.gridHdr + (long long)s * X.gridStride);
+    G.bm = g;
+    G.wpre = (const unsigned short*)(g + nbm);
+    const unsigned* gm = g + nbm + (nbm + 2) / 2;
+    G.ns = (int)gm[0];
+    G.hc = (int)gm[1];
+    G.tab = (const unsigned short*)(gm + 2);
+    G.zscale = (float)G.ns * P.zs_inv_range;
+  }
+  return G;
 }
 
 // ============================================================================================
@@ -1533,14 +1624,12 @@ __global__ void __launch_bounds__(256) k_desc_mark(
     if (finite3(o.x, o.y, o.z)) {
       const long long base = scan_off[s];
       const float4* so = sorted + base;
-      const unsigned* sk = X.sortedKey + base;
-      const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
-      const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+      const ScanGrid G = scan_grid(X, s, base, P);
       const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
       const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
       for (int r = cy0 + w; r <= cy1; r += 8) {
         int b, e;
-        row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
+        G.row_span(r, cx0, cx1, b, e);
         for (int i0 = b; i0 < e; i0 += 32) {
           const int i = i0 + lane;
           bool isn = false;
@@ -1621,9 +1710,7 @@ __global__ void __launch_bounds__(256) k_density(
   const long long base = scan_off[s];
   const float4* so = sorted + base;
   int* rh = rho + base;
-  const unsigned* sk = X.sortedKey + base;
-  const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
-  const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+  const ScanGrid G = scan_grid(X, s, base, P);
   const int nx = P.sg_nx, ny = P.sg_ny;
   unsigned ntest = 0, nmark = 0;  // per thread: at most 65,535 candidates per marked point, a few marked points
   // blockIdx.y strides over the scan's tiles: dense scans are shared by several blocks
@@ -1656,15 +1743,29 @@ __global__ void __launch_bounds__(256) k_density(
       const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, nx);
       const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, ny);
       int cnt = 0;
-      for (int r = cy0; r <= cy1; r++) {
-        int b, e;
-        row_span(sk, rs, ct, nx, r, cx0, cx1, P.sg_bx, b, e);
-        for (int j = b; j < e; j++) {
-          const float4 q = so[j];
-          // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
-          if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+      if (G.bm && G.ns > 1) {  // per cell, only the z slabs the density sphere reaches
+        const float zlo = p.z - P.rhopad, zhi = p.z + P.rhopad;
+        for (int r = cy0; r <= cy1; r++)
+          for (int c = cx0; c <= cx1; c++) {
+            int b, e;
+            G.cell_slab_span(r * nx + c, zlo, zhi, b, e);
+            for (int j = b; j < e; j++) {
+              const float4 q = so[j];
+              // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
+              if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+            }
+            ntest += (unsigned)(e - b);
+          }
+      } else {
+        for (int r = cy0; r <= cy1; r++) {
+          int b, e;
+          G.row_span(r, cx0, cx1, b, e);
+          for (int j = b; j < e; j++) {
+            const float4 q = so[j];
+            if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+          }
+          ntest += (unsigned)(e - b);
         }
-        ntest += (unsigned)(e - b);
       }
       rh[i] = cnt;
       nmark++;
@@ -1823,16 +1924,14 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     }
     const float2 ax = axes[rank];  // normalised x_axis = (ax.x, ax.y, -0)
     const float4* so = sorted + base;
-    const unsigned* sk = X.sortedKey + base;
-    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
-    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+    const ScanGrid G = scan_grid(X, s, base, P);
     const int* rh = rho + base;
     const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
     for (int r0 = cy0; off < 0 && r0 <= cy1; r0 += 32) {  // at most ~12 rows: one pass
       if (w == 0) {
         int b = 0, e = 0;
-        if (r0 + lane <= cy1) row_span(sk, rs, ct, P.sg_nx, r0 + lane, cx0, cx1, P.sg_bx, b, e);
+        if (r0 + lane <= cy1) G.row_span(r0 + lane, cx0, cx1, b, e);
         int inc = e - b;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -2221,15 +2320,13 @@ __global__ void __launch_bounds__(256) k_boundary_support(
     if (!finite3(o.x, o.y, o.z)) continue;
     const long long base = scan_off[s];
     const float4* so = sorted + base;
-    const unsigned* sk = X.sortedKey + base;
-    const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
-    const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+    const ScanGrid G = scan_grid(X, s, base, P);
     const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
     unsigned long long cnt = 0;
     for (int r = cy0 + w; r <= cy1; r += 8) {
       int b, e;
-      row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
+      G.row_span(r, cx0, cx1, b, e);
       for (int i = b + lane; i < e; i += 32) {
         const float4 q = so[i];
         if (on_boundary(B, 2, l2_simple(o.x, o.y, o.z, q.x, q.y, q.z))) cnt++;
@@ -2248,9 +2345,7 @@ __global__ void __launch_bounds__(256) k_boundary_density(
   const int n = surfN[s];
   const long long base = scan_off[s];
   const float4* so = sorted + base;
-  const unsigned* sk = X.sortedKey + base;
-  const int* rs = X.rowStart + (long long)s * (P.sg_ny + 1);
-  const unsigned short* ct = (X.cellTab && X.tabOk[s]) ? X.cellTab + (long long)s * X.ncells1 : nullptr;
+  const ScanGrid G = scan_grid(X, s, base, P);
   unsigned long long cnt = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     if (rho[base + i] >= 0) continue;
@@ -2259,7 +2354,7 @@ __global__ void __launch_bounds__(256) k_boundary_density(
     const int cy0 = surf_cell(p.y - P.rhopad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(p.y + P.rhopad, P.sy0, P.sg_inv, P.sg_ny);
     for (int r = cy0; r <= cy1; r++) {
       int b, e;
-      row_span(sk, rs, ct, P.sg_nx, r, cx0, cx1, P.sg_bx, b, e);
+      G.row_span(r, cx0, cx1, b, e);
       for (int j = b; j < e; j++) {
         const float4 q = so[j];
         if (on_boundary(B, 3, l2_simple(p.x, p.y, p.z, q.x, q.y, q.z))) cnt++;
