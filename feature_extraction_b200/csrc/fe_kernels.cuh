@@ -1559,6 +1559,14 @@ struct ScanGrid {                 // one scan's view of the index
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] <= khi) lo = mid + 1; else hi = mid; }
     e = lo;
   }
+  // span of one cell restricted to slabs [l0, l1] (index path only)
+  __device__ __forceinline__ void cell_slabs(int cell, int l0, int l1, int& b, int& e) const {
+    const unsigned bits = bm[cell >> 5];
+    if (!((bits >> (cell & 31)) & 1u)) { b = e = 0; return; }
+    const int rk = (int)wpre[cell >> 5] + __popc(bits & ((1u << (cell & 31)) - 1u));
+    b = (int)tab[rk * ns + l0];
+    e = (int)tab[rk * ns + l1 + 1];
+  }
   // span of one cell restricted to the slabs that [zlo, zhi] touches (index path only)
   __device__ __forceinline__ void cell_slab_span(int cell, float zlo, float zhi, int& b, int& e) const {
     const unsigned bits = bm[cell >> 5];
@@ -1736,8 +1744,10 @@ __global__ void __launch_bounds__(256) k_density(
       off += __popc(mk[k]);
     }
     __syncthreads();
-    for (int t = tid; t < m; t += 256) {
-      const int i = t0 + (int)s_list[t];
+    for (int tw = (tid & ~31); tw < m; tw += 256) {   // a warp takes 32 consecutive marked points
+      const int t = tw + lane;
+      const bool act = t < m;
+      const int i = t0 + (int)s_list[act ? t : tw];
       const float4 p = so[i];
       // cells reached by the density radius (>= 1 cell each way; more only if the grid was capped)
       const int cx0 = surf_cell(p.x - P.rhopad, P.sx0, P.sg_inv, nx), cx1 = surf_cell(p.x + P.rhopad, P.sx0, P.sg_inv, nx);
@@ -1745,17 +1755,38 @@ __global__ void __launch_bounds__(256) k_density(
       int cnt = 0;
       if (G.bm && G.ns > 1) {  // per cell, only the z slabs the density sphere reaches
         const float zlo = p.z - P.rhopad, zhi = p.z + P.rhopad;
-        for (int r = cy0; r <= cy1; r++)
-          for (int c = cx0; c <= cx1; c++) {
-            int b, e;
-            G.cell_slab_span(r * nx + c, zlo, zhi, b, e);
-            for (int j = b; j < e; j++) {
-              const float4 q = so[j];
-              // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
-              if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+        // The 32 points are consecutive in (cell, slab) order, so they mostly share their cell and their slabs:
+        // the warp sweeps the UNION of their neighbourhoods together — every lane tests every candidate
+        // (the exact predicate rejects what lies outside its own sphere), all loads are broadcasts, the
+        // loops are uniform.  Only a warp that straddles distant cells falls back to per-lane sweeps.
+        const int ux0 = __reduce_min_sync(FE_FULL, cx0), ux1 = __reduce_max_sync(FE_FULL, cx1);
+        const int uy0 = __reduce_min_sync(FE_FULL, cy0), uy1 = __reduce_max_sync(FE_FULL, cy1);
+        if ((ux1 - ux0 + 1) * (uy1 - uy0 + 1) <= 16) {
+          const int l0 = __reduce_min_sync(FE_FULL, z_slab(zlo, G.zs0, G.zscale, G.ns));
+          const int l1 = __reduce_max_sync(FE_FULL, z_slab(zhi, G.zs0, G.zscale, G.ns));
+          for (int r = uy0; r <= uy1; r++)
+            for (int c = ux0; c <= ux1; c++) {
+              int b, e;
+              G.cell_slabs(r * nx + c, l0, l1, b, e);
+              for (int j = b; j < e; j++) {
+                const float4 q = so[j];
+                // FLANN evaluates dist(query, point): query = the neighbour whose density is wanted
+                if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+              }
+              if (act) ntest += (unsigned)(e - b);
             }
-            ntest += (unsigned)(e - b);
-          }
+        } else {
+          for (int r = cy0; r <= cy1; r++)
+            for (int c = cx0; c <= cx1; c++) {
+              int b, e;
+              G.cell_slab_span(r * nx + c, zlo, zhi, b, e);
+              for (int j = b; j < e; j++) {
+                const float4 q = so[j];
+                if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
+              }
+              if (act) ntest += (unsigned)(e - b);
+            }
+        }
       } else {
         for (int r = cy0; r <= cy1; r++) {
           int b, e;
@@ -1764,9 +1795,10 @@ __global__ void __launch_bounds__(256) k_density(
             const float4 q = so[j];
             if (l2_simple(p.x, p.y, p.z, q.x, q.y, q.z) < P.rho2f) cnt++;
           }
-          ntest += (unsigned)(e - b);
+          if (act) ntest += (unsigned)(e - b);
         }
       }
+      if (!act) continue;
       rh[i] = cnt;
       nmark++;
     }
