@@ -19,8 +19,24 @@ using namespace fe;
 
 namespace {
 
+// Small sub-batches (a single scan per callback is how the reference runs, src:72) are launch-bound: ~17 dependent
+// launches.  Their whole chain — staging copies, kernels, result copies — is captured once per shape into a CUDA
+// graph and replayed (fe_process_batch, sub-batches of at most GRAPH_MAX_SCANS scans).
+constexpr int GRAPH_MAX_SCANS = 16;
+struct GraphKey {
+  int nscans, nch, by, k1flags, stride, xo, yo, zo;
+  int desc, wantKc, bnd, epoch;
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec = nullptr;  // null: the shape has been seen once (run eagerly, so that every lazy init is done)
+  int64_t launches = 0;
+};
+
 struct Slot {
   cudaStream_t stream = nullptr;
+  std::vector<GraphEntry> graphs;
   int64_t capPts = 0;
   int capScans = 0, capChunks = 0;
   int64_t capKp = 0;
@@ -91,6 +107,9 @@ struct fe_ctx {
   bool stageTiming = false;   // serialise the stages and time each with CUDA events (fe_enable_stage_timing)
   bool gridClustering = false;  // fe_debug_force_grid_clustering: K2 through the grid-based kernels only
   bool recordOutput = false;  // descriptors leave as FE_RECORD_FLOATS-float PointDescriptor records
+  int epoch = 0;              // bumped by every setting that changes what a captured graph would do
+  bool useGraphs = true;      // fe_debug_enable_graphs
+  int64_t graphReplays = 0;
   int angleLibm = 0;          // fe_set_angle_libm
   double bndEps = 0.0;        // fe_enable_boundary_report: > 0 = count the pairs within bndEps of every radius
   std::vector<int64_t> bndCounts;  // [scan][4] of the last batch call
@@ -250,6 +269,7 @@ void free_slot(Slot& s) {
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
   for (void* p : hv) if (p) cudaFreeHost(p);
   for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+  for (GraphEntry& g : s.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (s.evDone) cudaEventDestroy(s.evDone);
   if (s.evT0) cudaEventDestroy(s.evT0);
   if (s.evT1) cudaEventDestroy(s.evT1);
@@ -330,8 +350,17 @@ std::string err_bits(int e) {
 
 // Host-side staging of the small per-scan arrays of a sub-batch.  offs are absolute offsets of
 // the caller's array; the device sees offsets relative to the first point of the sub-batch.
+// the device copies of the staged arrays (from the pinned mirrors: the same addresses every call, so the copies can
+// live inside a captured graph)
+int stage_scans_copy(fe_ctx* ctx, Slot& s, int nscans, bool deferRot) {
+  CK(cudaMemcpyAsync(s.d_scan_off, s.h_scan_off, (nscans + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+  CK(cudaMemcpyAsync(s.d_chunk_off, s.h_chunk_off, (nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  if (!deferRot) CK(cudaMemcpyAsync(s.d_rot, s.h_rot, (size_t)nscans * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+  return FE_OK;
+}
+
 int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int nscans, int64_t* nptsOut, int* nchOut,
-                bool deferRot = false) {
+                bool deferRot = false, bool copy = true) {
   // the pinned mirrors hold capScans(+1) entries: check before the first write
   if (nscans > s.capScans) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_scans_per_call");
   const int64_t o0 = offs[0];
@@ -353,9 +382,7 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
   *nptsOut = offs[nscans] - o0;
   *nchOut = nch;
   if (nch > s.capChunks) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds the chunk capacity");
-  CK(cudaMemcpyAsync(s.d_scan_off, s.h_scan_off, (nscans + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
-  CK(cudaMemcpyAsync(s.d_chunk_off, s.h_chunk_off, (nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-  if (!deferRot) CK(cudaMemcpyAsync(s.d_rot, s.h_rot, (size_t)nscans * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+  if (copy) return stage_scans_copy(ctx, s, nscans, deferRot);
   return FE_OK;
 }
 
@@ -504,10 +531,14 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, c
   ctx->launches += 2;
 }
 
+// blocks per scan of K4c: about one per 8k points of an average scan (a dense scan's halo is tens of tiles)
+int density_blocks_per_scan(int nscans, int64_t npts) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(16, npts / std::max(nscans, 1) / 8192 + 1));
+}
+
 void launch_density(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int64_t npts) {
   if (nscans <= 0) return;
-  // blocks per scan: about one per 8k points of an average scan (a dense scan's halo is tens of tiles)
-  const int by = (int)std::max<int64_t>(1, std::min<int64_t>(16, npts / std::max(nscans, 1) / 8192 + 1));
+  const int by = density_blocks_per_scan(nscans, npts);
   k_density<<<dim3((unsigned)nscans, (unsigned)by), 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, s.d_surfN, s.d_rho, s.d_ctr->dens_work);
   ctx->launches++;
 }
@@ -582,7 +613,7 @@ int ensure_bnd(fe_ctx* ctx, Slot& s) {
 // `fromStage`: 0 = K1 first; 1 = crop/cropMeta/cropCnt already filled by the caller.
 int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int64_t npts, int nch,
                      int k1flags, bool doDesc, bool singleRing, bool wantKc, RawLayout lay = RawLayout{nullptr, 0, 0, 0, 0},
-                     const double* lateRp = nullptr) {
+                     const double* lateRp = nullptr, bool recordDone = true) {
   DevParams& P = ctx->dp;
   s.nev = 0;
   mark(ctx, s, "begin");
@@ -680,7 +711,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaMemcpyAsync(s.h_kpOff, s.d_kpOff, (size_t)(nscans + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   if (bnd) CK(cudaMemcpyAsync(s.h_bnd, s.d_bnd, (size_t)nscans * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-  CK(cudaEventRecord(s.evDone, s.stream));
+  if (recordDone) CK(cudaEventRecord(s.evDone, s.stream));
   CK(cudaGetLastError());
   return FE_OK;
 }
@@ -906,6 +937,7 @@ int fe_set_params(fe_ctx_t* ctx, const fe_params_t* params) {
   if (!ctx || !params) return FE_ERR_INVALID;
   cudaSetDevice(ctx->device);
   for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
+  ctx->epoch++;
   return derive_params(ctx, *params);
 }
 
@@ -925,6 +957,7 @@ void fe_destroy(fe_ctx_t* ctx) {
 int fe_enable_cloud_outputs(fe_ctx_t* ctx, int32_t enable) {
   if (!ctx) return FE_ERR_INVALID;
   ctx->cloudOutputs = enable != 0;
+  ctx->epoch++;
   return FE_OK;
 }
 
@@ -932,6 +965,7 @@ int fe_enable_stage_timing(fe_ctx_t* ctx, int32_t enable) {
   if (!ctx) return FE_ERR_INVALID;
   for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
   ctx->stageTiming = enable != 0;
+  ctx->epoch++;
   return FE_OK;
 }
 
@@ -939,6 +973,7 @@ int fe_enable_record_output(fe_ctx_t* ctx, int32_t enable) {
   if (!ctx) return FE_ERR_INVALID;
   for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
   ctx->recordOutput = enable != 0;
+  ctx->epoch++;
   return FE_OK;
 }
 
@@ -947,6 +982,7 @@ int fe_set_angle_libm(fe_ctx_t* ctx, int32_t mode) {
   for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
   ctx->angleLibm = mode;
   ctx->dp.angle_libm = mode;
+  ctx->epoch++;
   return FE_OK;
 }
 
@@ -955,6 +991,7 @@ int fe_enable_boundary_report(fe_ctx_t* ctx, double eps_m) {
   for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
   ctx->bndEps = eps_m > 0.0 ? eps_m : 0.0;
   ctx->bndCounts.clear();
+  ctx->epoch++;
   return FE_OK;
 }
 
@@ -1042,15 +1079,64 @@ static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int st
     }
     const int ns = last - first;
     int64_t np2; int nch;
-    st = stage_scans(ctx, s, scan_offsets + first, roll_pitch + 2 * first, ns, &np2, &nch);
+    const bool graphable = ctx->useGraphs && !ctx->stageTiming && ns <= GRAPH_MAX_SCANS;
+    st = stage_scans(ctx, s, scan_offsets + first, roll_pitch + 2 * first, ns, &np2, &nch, false, !graphable);
     if (st) return st;
     if (npts > 0)
       CK(cudaMemcpyAsync(s.d_pts, points + scan_offsets[first] * (int64_t)stride, (size_t)npts * (size_t)stride, cudaMemcpyHostToDevice, s.stream));
     const bool wantKc = ctx->cloudOutputs;
     if (wantKc) { st = ensure_kc(ctx, s); if (st) return st; }
     RawLayout lay = {isFloat4 ? nullptr : (const unsigned char*)s.d_pts, stride, xo, yo, zo};
-    st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, wantKc, lay);
-    if (st) return st;
+    const int k1flags = F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0);
+    if (!graphable) {
+      st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay);
+      if (st) return st;
+    } else {
+      // every allocation the pipeline may need happens before a capture starts
+      if (desc) { st = ensure_rowstart(ctx, s, ns); if (st) return st; }
+      if (ctx->bndEps > 0.0) { st = ensure_bnd(ctx, s); if (st) return st; }
+      GraphKey key;
+      memset(&key, 0, sizeof key);
+      key.nscans = ns; key.nch = nch; key.by = density_blocks_per_scan(ns, npts); key.k1flags = k1flags;
+      key.stride = isFloat4 ? 0 : stride; key.xo = xo; key.yo = yo; key.zo = zo;
+      key.desc = desc; key.wantKc = wantKc; key.bnd = ctx->bndEps > 0.0; key.epoch = ctx->epoch;
+      GraphEntry* ge = nullptr;
+      for (GraphEntry& g : s.graphs) if (g.key == key) { ge = &g; break; }
+      if (ge && ge->exec) {  // replay
+        CK(cudaGraphLaunch(ge->exec, s.stream));
+        ctx->launches += ge->launches;
+        ctx->graphReplays++;
+      } else if (!ge) {      // first sighting of the shape: eager, so that every lazily initialised piece exists
+        st = stage_scans_copy(ctx, s, ns, false);
+        if (st) return st;
+        st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay, nullptr, false);
+        if (st) return st;
+        if (s.graphs.size() >= 16) {  // drop the oldest shape
+          if (s.graphs[0].exec) cudaGraphExecDestroy(s.graphs[0].exec);
+          s.graphs.erase(s.graphs.begin());
+        }
+        GraphEntry e; e.key = key;
+        s.graphs.push_back(e);
+      } else {               // second sighting: capture, instantiate, launch
+        const int64_t l0 = ctx->launches;
+        CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        st = stage_scans_copy(ctx, s, ns, false);
+        if (st == FE_OK) st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay, nullptr, false);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(s.stream, &graph);
+        if (st) { if (graph) cudaGraphDestroy(graph); return st; }
+        if (ce != cudaSuccess) return fail(ctx, FE_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ci != cudaSuccess) return fail(ctx, FE_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ci));
+        ge->exec = exec;
+        ge->launches = ctx->launches - l0;
+        CK(cudaGraphLaunch(exec, s.stream));
+        ctx->graphReplays++;
+      }
+      CK(cudaEventRecord(s.evDone, s.stream));
+    }
     s.busy = true; s.nscans = ns; s.npts = npts; s.firstScan = first;
     nsub++;
     // the other slot's sub-batch was enqueued earlier: finalise it while this one runs
@@ -1661,6 +1747,16 @@ int fe_debug_force_grid_clustering(fe_ctx_t* ctx, int32_t enable) {
   if (!ctx) return FE_ERR_INVALID;
   for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) CK(cudaStreamSynchronize(ctx->slot[k].stream));
   ctx->gridClustering = enable != 0;
+  ctx->epoch++;
+  return FE_OK;
+}
+
+// debug / test hook: switch the CUDA-graph replay of small sub-batches off (eager launches) or on; out[0] (nullable)
+// receives the number of graph replays so far
+int fe_debug_enable_graphs(fe_ctx_t* ctx, int32_t enable, int64_t* replays) {
+  if (!ctx) return FE_ERR_INVALID;
+  ctx->useGraphs = enable != 0;
+  if (replays) *replays = ctx->graphReplays;
   return FE_OK;
 }
 

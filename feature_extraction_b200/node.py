@@ -311,6 +311,12 @@ class FeatureExtractionNode:
         self._check(N.lib().fe_debug_h2d_probe(self._ctx, _ptr(host_array), host_array.nbytes, C.byref(ms)))
         return float(ms.value)
 
+    def enableGraphs(self, enable=True):
+        """Test hook: CUDA-graph replay of small sub-batches on/off; -> graph replays so far."""
+        n = C.c_int64(0)
+        self._check(N.lib().fe_debug_enable_graphs(self._ctx, 1 if enable else 0, C.byref(n)))
+        return int(n.value)
+
     def forceGridClustering(self, enable=True):
         """Test hook: K2 through the grid-based kernels only (the run-based kernel's fallback and cross-check)."""
         self._check(N.lib().fe_debug_force_grid_clustering(self._ctx, 1 if enable else 0))

@@ -329,3 +329,50 @@ def test_cloud_outputs_across_sub_batches_and_shards(ob, synth):
     for s in range(37):
         assert bits_equal(cloud[co[s]:co[s + 1]], want[s]["cloud"]), s
         assert bits_equal(kcloud[kco[s]:kco[s + 1]], want[s]["keypoint_cloud"]), s
+
+
+def test_single_scan_calls_replay_a_captured_graph(ob, synth):
+    """The reference's deployment is one scan per callback (src:72, ros::spin): small sub-batches are captured
+    into a CUDA graph per shape and replayed.  Replays, eager launches and the oracle agree bit for bit; a
+    parameter change or another output mode invalidates the captured graphs."""
+    from feature_extraction_b200 import FeatureExtractionNode
+    P = ob.launch_playback()
+    nd = FeatureExtractionNode(to_fe_params(P), max_points=1 << 18, max_scans=4, max_keypoints=1024)
+    pts, offs, rp = synth.generate(1, 6, scan_index_base=9400)
+    want = [ob.process_scan(P, pts[offs[s]:offs[s + 1]], rp[s, 0], rp[s, 1], mode=1) for s in range(6)]
+    one = np.array([0, 0], np.int64)
+    for rep in range(3):
+        for s in range(6):
+            sc = pts[offs[s]:offs[s + 1]]
+            one[1] = len(sc)
+            ko, kp, d = nd.processBatch(sc, one, rp[s:s + 1])
+            assert bits_equal(kp, want[s]["keypoints"]) and bits_equal(d, want[s]["descriptors"]), (rep, s)
+    replays = nd.enableGraphs(True)
+    assert replays >= 6          # scans of equal chunk count share a graph from their second sighting on
+    nd.enableGraphs(False)       # eager launches give the same
+    sc = pts[offs[2]:offs[3]]
+    one[1] = len(sc)
+    ko, kp, d = nd.processBatch(sc, one, rp[2:3])
+    assert bits_equal(kp, want[2]["keypoints"]) and bits_equal(d, want[2]["descriptors"])
+    assert nd.enableGraphs(True) == replays
+    # new parameters: the old graphs must not be replayed
+    P2 = ob.node_default()
+    nd.set_params(to_fe_params(P2))
+    w2 = ob.process_scan(P2, sc, rp[2, 0], rp[2, 1], mode=1)
+    for rep in range(3):
+        ko, kp, d = nd.processBatch(sc, one, rp[2:3])
+        assert bits_equal(kp, w2["keypoints"]) and bits_equal(d, w2["descriptors"])
+    nd.enableCloudOutputs(True)
+    for rep in range(3):
+        ko, kp, d = nd.processBatch(sc, one, rp[2:3])
+        co, cloud, kco, kcloud = nd.cloudOutputs(1)
+        assert bits_equal(kp, w2["keypoints"]) and bits_equal(cloud, w2["cloud"]) and bits_equal(kcloud, w2["keypoint_cloud"])
+    # a scan without keypoints and an empty scan through the same context
+    far = sc.copy()
+    far[:, 0] -= 500.0
+    for rep in range(3):
+        ko, kp, d = nd.processBatch(far, one, rp[2:3])
+        assert ko[-1] == 0
+    ko, kp, d = nd.processBatch(np.zeros((0, 4), np.float32), np.zeros(2, np.int64), rp[2:3])
+    assert ko[-1] == 0
+    nd.close()
