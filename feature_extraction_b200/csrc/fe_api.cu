@@ -81,6 +81,7 @@ struct Slot {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   bool sideK4a = false;  // the pipeline in flight uses the side stream
   int lastNch = 0;
+  int64_t maxScanPts = 0;  // largest scan of the staged sub-batch
   // bookkeeping of the sub-batch in flight
   int nscans = 0;
   int64_t npts = 0;
@@ -107,6 +108,7 @@ struct fe_ctx {
   bool stageTiming = false;   // serialise the stages and time each with CUDA events (fe_enable_stage_timing)
   bool gridClustering = false;  // fe_debug_force_grid_clustering: K2 through the grid-based kernels only
   bool recordOutput = false;  // descriptors leave as FE_RECORD_FLOATS-float PointDescriptor records
+  int numSms = 148;           // cudaDevAttrMultiProcessorCount of the context's device (grids are sized in resident waves)
   int epoch = 0;              // bumped by every setting that changes what a captured graph would do
   bool useGraphs = true;      // fe_debug_enable_graphs
   int64_t graphReplays = 0;
@@ -367,9 +369,11 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
   if (o0 < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must not be negative");
   if (offs[nscans] - o0 > s.capPts) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds max_points_per_call");
   int nch = 0;
+  s.maxScanPts = 0;
   for (int i = 0; i < nscans; i++) {
     const int64_t n = offs[i + 1] - offs[i];
     if (n < 0) return fail(ctx, FE_ERR_INVALID, "scan_offsets must be non-decreasing");
+    s.maxScanPts = std::max(s.maxScanPts, n);
     s.h_scan_off[i] = (long long)(offs[i] - o0);
     s.h_chunk_off[i] = nch;
     nch += (int)((n + CH - 1) / CH);
@@ -470,26 +474,25 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist_warp, DW_WARPS * 32, desc_warp_smem_bytes()) != cudaSuccess) v = 2;
       return v;
     }();
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int nsm = ctx->numSms;
     k_desc_hist_warp<<<nsm * std::max(perSmW, 1), DW_WARPS * 32, desc_warp_smem_bytes(), s.stream>>>(
         s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap,
         s.d_keyA, s.d_kpNbrOff, s.d_kpRank, s.d_desc, descStride, descOff, s.d_ctr);
     ctx->launches++;
   }
 #define FE_DESC_LIST nullptr, nullptr
-  k_desc_hist<256, DCAP, DW_CAP, false, true><<<std::min(gridKp, 148 * std::max(perSm, 1)), 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<256, DCAP, DW_CAP, false, true><<<std::min(gridKp, ctx->numSms * std::max(perSm, 1)), 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
 #define FE_DESC_LIST s.d_kpListM, &s.d_ctr->n_list_m
-  k_desc_hist<512, DCAP_M, DCAP, false, false><<<std::min(gridKp, 148 * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<512, DCAP_M, DCAP, false, false><<<std::min(gridKp, ctx->numSms * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
 #define FE_DESC_LIST s.d_kpListL, &s.d_ctr->n_list_l
-  k_desc_hist<512, DCAP_L, DCAP_M, true, false><<<std::min(gridKp, 148), 512, desc_smem_bytes(DCAP_L, 512), s.stream>>>(FE_DESC_ARGS);
+  k_desc_hist<512, DCAP_L, DCAP_M, true, false><<<std::min(gridKp, ctx->numSms), 512, desc_smem_bytes(DCAP_L, 512), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
 #undef FE_DESC_ARGS
   ctx->launches += 3;
   if (records) {
-    k_record_frame<<<148 * 2, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpOff, nscans, s.d_desc, descStride, FE_DESC_LEN);
+    k_record_frame<<<ctx->numSms * 2, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpOff, nscans, s.d_desc, descStride, FE_DESC_LEN);
     ctx->launches++;
   }
 }
@@ -503,7 +506,7 @@ void launch_desc_mark(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_mark, 256, MARK_LCAP * sizeof(unsigned)) != cudaSuccess) v = 4;
     return v;
   }();
-  gridKp = std::min(gridKp, 148 * std::max(perSm, 1));
+  gridKp = std::min(gridKp, ctx->numSms * std::max(perSm, 1));
   k_desc_mark<<<gridKp, 256, MARK_LCAP * sizeof(unsigned), s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted,
                                                                        surf_index(ctx, s), s.d_scan_off, P, s.d_rho, s.d_kpNbr,
                                                                        s.d_keyA, nbrCap, s.d_kpNbrOff, s.d_ctr);
@@ -519,7 +522,11 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, c
     k_surface_grid_cells<NT_SURF><<<nscans, NT_SURF, surf_cells_smem_bytes(ncells), q>>>(
         s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_kpOut, s.d_kpOff, s.d_sorted, s.d_rho,
         s.d_surfN, s.d_ctr, s.d_ovfSurf, s.d_gridHdr, grid_hdr_bytes(ncells), s.d_tabOk);
-    k_surface_grid<<<std::min(nscans, 148 * 2), NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
+    ctx->launches++;
+    // the radix kernel only takes scans the counting sort defers: more than 65,535 surface points or more halo
+    // cells than counters — impossible when every scan is small and the grid has no more cells than counters
+    if (s.maxScanPts <= 65535 && ncells <= GRID_TAB_CAP) return;
+    k_surface_grid<<<std::min(nscans, ctx->numSms * 2), NT2, 0, q>>>(s.d_surf, s.d_surfCnt, s.d_scan_off, s.d_chunk_off, P, s.d_keyA,
                                                                    s.d_keyB, s.d_valA, s.d_valB, s.d_sorted, s.d_sortedKey,
                                                                    s.d_rowStart, s.d_surfN, s.d_ctr, s.d_ovfSurf, &s.d_ctr->ovf_surf,
                                                                    s.d_tabOk, s.d_rho);
@@ -528,7 +535,7 @@ void launch_surface_grid(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, c
                                                  s.d_valB, s.d_sorted, s.d_sortedKey, s.d_rowStart, s.d_surfN, s.d_ctr, nullptr, nullptr,
                                                  s.d_tabOk, s.d_rho);
   }
-  ctx->launches += 2;
+  ctx->launches++;
 }
 
 // blocks per scan of K4c: about one per 8k points of an average scan (a dense scan's halo is tens of tiles)
@@ -552,7 +559,7 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
   // not fit its shared memory to a list; the large shared-memory one takes that list; what does not
   // fit there either goes to the instantiation whose per-entry arrays live in global memory.
   const DevParams& P = ctx->dp;
-  const int gridL = std::min(nscans, 148), gridG = std::min(nscans, NGLOBAL);
+  const int gridL = std::min(nscans, ctx->numSms), gridG = std::min(nscans, NGLOBAL);
   const size_t smemG = cluster_smem_bytes_global(NT2);
   int* ovfR = &s.d_ctr->ovf_rings;
   int* ovfR2 = &s.d_ctr->ovf_rings2;
@@ -678,11 +685,11 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     // K4a runs after the keypoints are known: it only keeps the surface points a keypoint can reach
     launch_surface_grid(ctx, s, nscans, P, s.stream);
     mark(ctx, s, "K4a surface grid");
-    const int gridKp = 148 * 8;
+    const int gridKp = ctx->numSms * 8;
     launch_desc_mark(ctx, s, nscans, P, gridKp);
     mark(ctx, s, "K4b mark neighbours");
     if (bnd) {  // before K4c turns the marks in rho into densities
-      k_boundary_support<<<148 * 4, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, surf_index(ctx, s),
+      k_boundary_support<<<ctx->numSms * 4, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_sorted, surf_index(ctx, s),
                                                          s.d_scan_off, P, boundary_spec(ctx), s.d_bnd);
       if (npts > 0)
         k_boundary_density<<<nscans, 256, 0, s.stream>>>(s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, s.d_surfN, s.d_rho,
@@ -907,6 +914,7 @@ int fe_create(int device, const fe_params_t* params, const fe_limits_t* limits, 
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(FE_ERR_CUDA);
   if (prop.major != 10) return bail(FE_ERR_NO_DEVICE);  // built for sm_100a only
+  ctx->numSms = std::max(prop.multiProcessorCount, 1);
   if (cudaMalloc((void**)&ctx->d_lut, FE_DESC_LEN * sizeof(float)) != cudaSuccess) return bail(FE_ERR_CUDA);
   // 3DSC x-axes: boost::uniform_01<mt19937>(12345) draws 3k..3k+2 -> (x0, x1, -0) normalised
   ctx->axesCap = 1 << 16;
@@ -1014,7 +1022,7 @@ int fe_debug_libm_f32(fe_ctx_t* ctx, int32_t op, const float* a, const float* b,
     return done(fail(ctx, FE_ERR_CUDA, "fe_debug_libm_f32: out of device memory"));
   cudaMemcpy(da, a, (size_t)n * 4, cudaMemcpyHostToDevice);
   if (op == 0) cudaMemcpy(db, b, (size_t)n * 4, cudaMemcpyHostToDevice);
-  k_debug_libm_f32<<<148 * 8, 256>>>(op, da, db, dout, (long long)n);
+  k_debug_libm_f32<<<ctx->numSms * 8, 256>>>(op, da, db, dout, (long long)n);
   ctx->launches++;
   if (cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
     return done(fail(ctx, FE_ERR_CUDA, std::string("fe_debug_libm_f32: ") + cudaGetErrorString(cudaGetLastError())));
@@ -1097,7 +1105,7 @@ static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int st
       if (ctx->bndEps > 0.0) { st = ensure_bnd(ctx, s); if (st) return st; }
       GraphKey key;
       memset(&key, 0, sizeof key);
-      key.nscans = ns; key.nch = nch; key.by = density_blocks_per_scan(ns, npts); key.k1flags = k1flags;
+      key.nscans = ns; key.nch = nch; key.by = density_blocks_per_scan(ns, npts); key.k1flags = k1flags | ((s.maxScanPts > 65535) ? (1 << 16) : 0);
       key.stride = isFloat4 ? 0 : stride; key.xo = xo; key.yo = yo; key.zo = zo;
       key.desc = desc; key.wantKc = wantKc; key.bnd = ctx->bndEps > 0.0; key.epoch = ctx->epoch;
       GraphEntry* ge = nullptr;
@@ -1527,9 +1535,9 @@ int fe_estimate_descriptors(fe_ctx_t* ctx, const fe_point_t* cloud_full, int64_t
       cudaMemcpyAsync(s.d_kpOut, keypoints, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, q) != cudaSuccess)
     return restore(fail(ctx, FE_ERR_CUDA, "staging of the descriptor inputs failed"));
   launch_surface_grid(ctx, s, 1, P, s.stream);
-  launch_desc_mark(ctx, s, 1, P, 148 * 4);
+  launch_desc_mark(ctx, s, 1, P, ctx->numSms * 4);
   launch_density(ctx, s, 1, P, n);
-  launch_desc_hist(ctx, s, 1, P, 148 * 4, false);
+  launch_desc_hist(ctx, s, 1, P, ctx->numSms * 4, false);
   ctx->dp = saved;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, q));

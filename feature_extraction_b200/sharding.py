@@ -51,6 +51,19 @@ def gather_results(keypoint_offsets, keypoints, descriptors, dst=0):
     return concat_csr(out)
 
 
+def _parallel_copy(dst, src, threads=4, min_rows=4096):
+    """dst[:] = src with a few threads (numpy releases the GIL inside large copies): the descriptor block of a
+    100k-scan sweep is gigabytes, one thread moves it at a fraction of the host's memory bandwidth."""
+    n = len(src)
+    if n < min_rows or threads <= 1:
+        dst[:] = src
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    cuts = [n * i // threads for i in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda ab: np.copyto(dst[ab[0]:ab[1]], src[ab[0]:ab[1]]), zip(cuts[:-1], cuts[1:])))
+
+
 class SharedGather:
     """Host-side gather of per-rank CSR results through one POSIX shared-memory segment (ranks of ONE box).
 
@@ -65,9 +78,24 @@ class SharedGather:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         port = os.environ.get("MASTER_PORT", "0")
-        self.path = "/dev/shm/%s_%s" % (tag, port)
+        self.name = "%s_%s" % (tag, port)
+        self.path = None
         self.cap = 0
         self.mm = None
+
+    @staticmethod
+    def _pick_dir(nbytes):
+        """A directory every rank of the box sees with room for the segment: /dev/shm when it is large enough
+        (a container's default is 64 MB — writing past a tmpfs's size is a SIGBUS, not an exception), else /tmp."""
+        import os
+        for d in ("/dev/shm", "/tmp"):
+            try:
+                st = os.statvfs(d)
+                if st.f_bavail * st.f_frsize > nbytes * 1.2 + (64 << 20):
+                    return d
+            except OSError:
+                pass
+        return None
 
     def _all_counts(self, n_scans, n_kp):
         import torch
@@ -87,6 +115,17 @@ class SharedGather:
             return
         cap = max(int(nbytes * 1.25) + 4096, 1 << 20)
         self.mm = None
+        if self.path:
+            if self.rank == 0:
+                try:
+                    os.unlink(self.path)
+                except OSError:
+                    pass
+            self.path = None
+        d = self._pick_dir(cap)   # the same answer on every rank of the box
+        if d is None:
+            raise MemoryError("SharedGather: no shared directory with %d bytes free" % cap)
+        self.path = os.path.join(d, self.name)
         if self.rank == 0:
             with open(self.path, "wb") as f:
                 f.truncate(cap)
@@ -118,7 +157,8 @@ class SharedGather:
             offs[0] = 0
         self.mm[o_kp + k0 * 16: o_kp + (k0 + len(kp)) * 16].view(np.float32).reshape(-1, 4)[:] = kp
         if dl:
-            self.mm[o_d + k0 * dl * 4: o_d + (k0 + len(kp)) * dl * 4].view(np.float32).reshape(-1, dl)[:] = d
+            dst_d = self.mm[o_d + k0 * dl * 4: o_d + (k0 + len(kp)) * dl * 4].view(np.float32).reshape(-1, dl)
+            _parallel_copy(dst_d, d)
         dist.barrier()
         if self.rank != dst:
             return None
@@ -131,7 +171,7 @@ class SharedGather:
         self.mm = None
         if self.world > 1 and dist.is_initialized():
             dist.barrier()
-        if self.rank == 0:
+        if self.rank == 0 and self.path:
             try:
                 os.unlink(self.path)
             except OSError:

@@ -20,7 +20,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --config 2 --scans 2000 --steps 2 --warmup 1 --no-cpu-baseline > "$OUT/ncu_launches.log" 2>&1
 # one full-set capture of every kernel of one step
 timeout 900 ncu --set full --clock-control none --import-source on \
-  -k regex:"k_ring_runs|k_level_crop|k_surface_grid_cells|k_density|k_desc_hist|k_desc_mark|k_merge" -c 14 \
-  -f -o "$OUT/prof_full" python bench.py --config 2 --scans 1000 --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
-ncu -i "$OUT/prof_full.ncu-rep" --page raw --csv > "$OUT/ncu_full_raw_1000scans.csv" 2>/dev/null
+  -k regex:"k_ring_runs|k_level_crop|k_surface_grid_cells|k_density|k_desc_hist|k_desc_mark|k_merge" -c 20 \
+  -f -o "$OUT/prof_full" python bench.py --config 2 --scans 10000 --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
+ncu -i "$OUT/prof_full.ncu-rep" --page raw --csv > "$OUT/ncu_full_raw_10000scans.csv" 2>/dev/null
+python tools/parity_campaign.py > "$OUT/parity_campaign.log" 2>&1
+python tools/parity_campaign.py 100000 > "$OUT/parity_campaign_shift.log" 2>&1
 ls -la "$OUT"

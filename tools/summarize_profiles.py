@@ -2,7 +2,7 @@
 """Turn what tools/final_profile.sh left in gpurun_out/<tag>/ into the tracked files under profiles/:
     <tag>_bench_config{1,2,3,4}.json, <tag>_bench_reference_arm.json   (the un-profiled bench lines)
     <tag>_launches_config2_2000scans.csv + <tag>_launch_shares.md      (ncu launch list vs CUDA-event shares)
-    <tag>_ncu_full_raw_1000scans.csv + <tag>_ncu_summary.md            (ncu --set full extracts)
+    <tag>_ncu_full_raw_10000scans.csv + <tag>_ncu_summary.md            (ncu --set full extracts)
     dram_traffic.json                                                   (per-stage DRAM bytes, read by bench.py)
 usage: python tools/summarize_profiles.py <tag>
 """
@@ -46,7 +46,7 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r2_final"
     src = os.path.join(ROOT, "gpurun_out", tag)
     dst = os.path.join(ROOT, "profiles")
-    for name in ("bench_config1", "bench_config2", "bench_config3", "bench_config4", "bench_reference_arm"):
+    for name in ("bench_default", "bench_config1", "bench_config2", "bench_config3", "bench_config4", "bench_reference_arm"):
         p = os.path.join(src, name + ".json")
         if os.path.exists(p) and os.path.getsize(p) > 0:
             shutil.copy(p, os.path.join(dst, "%s_%s.json" % (tag, name)))
@@ -82,8 +82,8 @@ def main():
     open(os.path.join(dst, tag + "_launch_shares.md"), "w").write("\n".join(md) + "\n")
 
     # ---- full-set capture ----
-    rp = os.path.join(src, "ncu_full_raw_1000scans.csv")
-    shutil.copy(rp, os.path.join(dst, tag + "_ncu_full_raw_1000scans.csv"))
+    rp = os.path.join(src, "ncu_full_raw_10000scans.csv")
+    shutil.copy(rp, os.path.join(dst, tag + "_ncu_full_raw_10000scans.csv"))
     rows = list(csv.reader(open(rp, errors="replace")))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
@@ -102,10 +102,10 @@ def main():
         if u == "ms": x *= 1e3
         return x * scale
 
-    md = ["# %s — `ncu --set full --clock-control none` extracts, config 2, 1000 scans per launch" % tag, "",
+    md = ["# %s — `ncu --set full --clock-control none` extracts, config 2, 10000 scans per launch" % tag, "",
           "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_ring_runs|k_level_crop|k_surface_grid_cells|"
-          "k_density|k_desc_hist|k_desc_mark|k_merge\" -c 14 -o ... python bench.py --scans 1000 --steps 1 --warmup 0 --no-cpu-baseline` "
-          "(raw page: `%s_ncu_full_raw_1000scans.csv`; script `tools/final_profile.sh`).  Cold caches, serialised launches." % tag, "",
+          "k_density|k_desc_hist|k_desc_mark|k_merge\" -c 20 -o ... python bench.py --config 2 --scans 10000 --steps 1 --warmup 0 --no-cpu-baseline` "
+          "(raw page: `%s_ncu_full_raw_10000scans.csv`; script `tools/final_profile.sh`).  Cold caches, serialised launches." % tag, "",
           "| kernel | time µs | DRAM read MB | DRAM write MB | regs | grid×block | warps active % | DRAM % | issue active % | thr/inst | L2 hit % |",
           "|---|---|---|---|---|---|---|---|---|---|---|"]
     traffic = {}
@@ -129,13 +129,13 @@ def main():
             g(r, "smsp__thread_inst_executed_per_inst_executed.ratio"), g(r, "lts__t_sector_hit_rate.pct")))
         st = stage_of(k)
         if st:
-            t = traffic.setdefault(st, {"scans": 1000, "dram_bytes_per_launch": 0.0, "source": "profiles/%s_ncu_full_raw_1000scans.csv" % tag})
+            t = traffic.setdefault(st, {"scans": 10000, "dram_bytes_per_launch": 0.0, "source": "profiles/%s_ncu_full_raw_10000scans.csv" % tag})
             t["dram_bytes_per_launch"] += rd + wr
-    md += ["", "DRAM bytes per stage (read + write, all instantiations of the stage summed) against the algorithmic bytes of the bench, both per 1000 scans:", "",
+    md += ["", "DRAM bytes per stage (read + write, all instantiations of the stage summed) against the algorithmic bytes of the bench, both per 10000 scans:", "",
            "| stage | DRAM MB (ncu) | algorithmic MB | ratio |", "|---|---|---|---|"]
     B = bench["config"]["scans_per_gpu"]
     for st, t in traffic.items():
-        alg = bench["kernels"].get(st, {}).get("algorithmic_bytes", 0) * 1000.0 / B
+        alg = bench["kernels"].get(st, {}).get("algorithmic_bytes", 0) * 10000.0 / B
         md.append("| %s | %.1f | %.1f | %.2f |" % (st, t["dram_bytes_per_launch"] / 1e6, alg / 1e6, t["dram_bytes_per_launch"] / alg if alg else float("nan")))
     open(os.path.join(dst, tag + "_ncu_summary.md"), "w").write("\n".join(md) + "\n")
     json.dump(traffic, open(os.path.join(dst, "dram_traffic.json"), "w"), indent=1)
