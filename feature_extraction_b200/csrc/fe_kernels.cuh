@@ -1888,8 +1888,9 @@ __device__ __forceinline__ bool shape_context_contribution(const float4 o, const
 // (one row per lane), every thread sweeps the flattened candidate range and the true neighbours are
 // compacted into a list, so the expensive bin arithmetic runs on a dense list with no idle lanes.
 // Three instantiations share the keypoints by neighbour count: (NB_MIN, CAP] each; the LAST one also
-// takes keypoints beyond its CAP, whose sums then use shared-memory float atomics (order-free,
-// ~1e-7 relative) and are counted in DevCounters::desc_unordered.
+// takes keypoints beyond its CAP and handles their bins in groups that fit the workspace (one sweep of
+// the candidates per group), so they are bit-identical too; only a single bin holding more than CAP
+// contributions is summed with order-free float atomics (counted in DevCounters::desc_unordered).
 template <int NT, int CAP, int NB_MIN, bool LAST, bool DYN>
 __global__ void __launch_bounds__(NT) k_desc_hist(
     const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
@@ -1946,7 +1947,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const float4 o = kpOut[g];
     const long long base = scan_off[s];
     for (int i = tid; i < FE_DESC_LEN; i += NT) hist[i] = 0.0f;
-    if (tid == 0) { s_cnt = 0; if (!ordered) atomicAdd(&ctr->desc_unordered, 1); }
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
     if (rank >= axesCap) {
       if (tid == 0) atomicOr(&ctr->err, ERR_AXIS_CAP);
@@ -1960,6 +1961,127 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const int* rh = rho + base;
     const int cx0 = surf_cell(o.x - P.Rpad, P.sx0, P.sg_inv, P.sg_nx), cx1 = surf_cell(o.x + P.Rpad, P.sx0, P.sg_inv, P.sg_nx);
     const int cy0 = surf_cell(o.y - P.Rpad, P.sy0, P.sg_inv, P.sg_ny), cy1 = surf_cell(o.y + P.Rpad, P.sy0, P.sg_inv, P.sg_ny);
+    if (LAST && !ordered) {
+      // More contributions than the sort workspace holds: the bins are handled in GROUPS of consecutive bins whose
+      // contributions fit (counted first), one sweep of the candidates per group — so these keypoints, too, are summed
+      // in PCL's order.  Only a single bin with more than CAP contributions is summed with order-free atomics.
+      __shared__ int s_ge, s_base, s_nrec;
+      __shared__ float s_acc;
+      auto sweep = [&](auto&& fn) {  // fn(i, q, d2) for every neighbour of the keypoint
+        for (int r0 = cy0; r0 <= cy1; r0 += 32) {
+          __syncthreads();
+          if (w == 0) {
+            int b = 0, e = 0;
+            if (r0 + lane <= cy1) G.row_span(r0 + lane, cx0, cx1, b, e);
+            int inc = e - b;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int t = __shfl_up_sync(FE_FULL, inc, d);
+              if (lane >= d) inc += t;
+            }
+            s_spanB[lane] = b;
+            s_spanS[lane] = inc - (e - b);
+            if (lane == 31) { s_spanS[32] = inc; s_total = inc; }
+          }
+          __syncthreads();
+          const int ncand = s_total;
+          for (int t = tid; t < ncand; t += NT) {
+            int r = 0;
+#pragma unroll
+            for (int k = 16; k; k >>= 1) if (r + k < 32 && s_spanS[r + k] <= t) r += k;
+            const int i = s_spanB[r] + (t - s_spanS[r]);
+            const float4 q = so[i];
+            const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
+            if (d2 < P.R2f) fn(i, q, d2);
+          }
+        }
+        __syncthreads();
+      };
+      // (A) contributions per bin
+      sweep([&](int i, const float4& q, float d2) {
+        int bin; float wgt;
+        if (shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wgt)) atomicAdd(&binCnt[bin], 1);
+      });
+      // (B) exclusive prefix: binCnt[b] = first record of bin b
+      {
+        constexpr int PER = (FE_DESC_LEN + NT - 1) / NT;
+        int loc[PER];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+          const int bi = tid * PER + k;
+          loc[k] = (bi < FE_DESC_LEN) ? binCnt[bi] : 0;
+          sum += loc[k];
+        }
+        int tot;
+        int run = block_excl_scan<NT>(sum, &tot, s_scan);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+          const int bi = tid * PER + k;
+          if (bi < FE_DESC_LEN) binCnt[bi] = run;
+          run += loc[k];
+        }
+        if (tid == 0) s_nrec = tot;
+      }
+      __syncthreads();
+      const int nrec = s_nrec;
+      bool anyUnordered = false;
+      for (int gb = 0; gb < FE_DESC_LEN;) {
+        if (tid == 0) {  // the group: bins [gb, ge) with at most CAP contributions (at least one bin)
+          const int basep = binCnt[gb];
+          int ge = gb + 1;
+          while (ge < FE_DESC_LEN && ((ge + 1 < FE_DESC_LEN) ? binCnt[ge + 1] : nrec) - basep <= CAP) ge++;
+          s_ge = ge; s_base = basep; s_acc = 0.0f;
+        }
+        __syncthreads();
+        const int ge = s_ge, basep = s_base;
+        const int gcount = ((ge < FE_DESC_LEN) ? binCnt[ge] : nrec) - basep;
+        __syncthreads();
+        if (gcount > CAP) {  // one bin alone exceeds the workspace: order-free
+          anyUnordered = true;
+          sweep([&](int i, const float4& q, float d2) {
+            int bin; float wgt;
+            if (shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wgt) && bin == gb) atomicAdd(&s_acc, wgt);
+          });
+          if (tid == 0) out[gb] = s_acc;
+        } else if (gcount > 0) {
+          // records of the group, placed by bin as they are found (the bin's start doubles as its cursor)
+          sweep([&](int i, const float4& q, float d2) {
+            int bin; float wgt;
+            if (shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wgt) && bin >= gb && bin < ge) {
+              const int pos = atomicAdd(&binCnt[bin], 1) - basep;
+              keyB[pos] = ((unsigned long long)bin << 52) | ((unsigned long long)__float_as_uint(d2) << 20) |
+                          (unsigned long long)((unsigned)__float_as_int(q.w) & 0xFFFFFu);
+              wB[pos] = wgt;
+            }
+          });
+          // rank inside every bin (binCnt[b] is now the END of bin b; bin gb starts at the group's base)
+          for (int i = tid; i < gcount; i += NT) {
+            const unsigned long long k = keyB[i];
+            const int bin = (int)(k >> 52);
+            const int b0 = (bin > gb ? binCnt[bin - 1] : basep) - basep, e0 = binCnt[bin] - basep;
+            int smaller = 0;
+            for (int t = b0; t < e0; t++) smaller += (keyB[t] < k) ? 1 : 0;
+            keyA[b0 + smaller] = k;
+            wA[b0 + smaller] = wB[i];
+          }
+          __syncthreads();
+          for (int bin = gb + tid; bin < ge; bin += NT) {
+            const int b0 = (bin > gb ? binCnt[bin - 1] : basep) - basep, e0 = binCnt[bin] - basep;
+            float acc = 0.0f;
+            for (int t = b0; t < e0; t++) acc = __fadd_rn(acc, wA[t]);
+            out[bin] = acc;
+          }
+        } else {
+          for (int bin = gb + tid; bin < ge; bin += NT) out[bin] = 0.0f;
+        }
+        __syncthreads();
+        gb = ge;
+      }
+      if (anyUnordered && tid == 0) atomicAdd(&ctr->desc_unordered, 1);
+      __syncthreads();
+      continue;
+    }
     for (int r0 = cy0; off < 0 && r0 <= cy1; r0 += 32) {  // at most ~12 rows: one pass
       if (w == 0) {
         int b = 0, e = 0;

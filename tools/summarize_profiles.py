@@ -58,7 +58,8 @@ def main():
     L = read_launches(lp)
     # every step starts with k_level_crop_ring; warm-up 1 + 2 steps: the third sequence is the last
     # device-resident step (the e2e phase with its 1024-scan sub-batches follows it)
-    starts = [i for i, (k, _) in enumerate(L) if "k_level_crop_ring" in k]
+    # a step = a run of K1 launches (one per scan range) followed by the other kernels
+    starts = [i for i, (k, _) in enumerate(L) if "k_level_crop_ring" in k and (i == 0 or "k_level_crop_ring" not in L[i - 1][0])]
     seq = L[starts[2]:starts[3]] if len(starts) > 3 else L[starts[-1]:]
     tot = sum(v for _, v in seq)
     md = ["# %s — ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`), config 2, 2000 scans per step" % tag, "",
@@ -109,15 +110,16 @@ def main():
           "| kernel | time µs | DRAM read MB | DRAM write MB | regs | grid×block | warps active % | DRAM % | issue active % | thr/inst | L2 hit % |",
           "|---|---|---|---|---|---|---|---|---|---|---|"]
     traffic = {}
-    seen_k1 = 0
+    seen_other = False
     for r in rows[2:]:
         if len(r) < len(hdr):
             continue
         k = r[col["Kernel Name"]]
         if "k_level_crop_ring" in k:
-            seen_k1 += 1
-            if seen_k1 > 1:
-                break  # the second step (e2e phase) starts here
+            if seen_other:
+                break  # the second step (e2e phase) starts here; a device step launches K1 in up to four scan ranges
+        else:
+            seen_other = True
         rd, wr = g(r, "dram__bytes_read.sum"), g(r, "dram__bytes_write.sum")
         grid = r[col["Grid Size"]].strip("()").split(",")[0].strip()
         blk = r[col["Block Size"]].strip("()").split(",")[0].strip()
