@@ -1365,13 +1365,14 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
   unsigned* halo = cnts + ((GRID_TAB_CAP + 2) / 2) + 16;  // one bit per cell
   unsigned short* wpre = (unsigned short*)(halo + nbm + 4);  // halo cells before every bit-map word
   __shared__ int sc[40];
-  __shared__ int s_n, s_hc;
+  __shared__ int s_n, s_hc, s_hl;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   constexpr int NW = NTS / 32;
   const long long base = scan_off[s];
   const int c0 = chunk_off[s];
   const int nch = chunk_off[s + 1] - c0;
   const int k0 = kpOff[s], k1 = kpOff[s + 1];
+  if (tid == 0) s_hl = 0;
   if (k1 == k0) {  // no keypoint: nothing of this scan's surface is ever looked at
     if (tid == 0) { surfN[s] = 0; tabOk[s] = 1; }
     return;
@@ -1437,7 +1438,11 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     return rk * NS + z_slab(z, P.zs0, zscale, NS);
   };
   // (2) count: the survivors of a chunk are contiguous; the chunks are cut into runs of 128 points that
-  //     are dealt to the warps, four 16-byte loads in flight per lane
+  //     are dealt to the warps, four 16-byte loads in flight per lane.  The halo points found (a few percent
+  //     of a sparse scan) are also listed — (piece position, slot) pairs in the unused tail of the counter
+  //     array — so that the scatter pass touches only them instead of streaming the surface a second time.
+  unsigned* hlist = cnts + ((nwords + 3) & ~3);
+  const int hlCap = max(0, ((GRID_TAB_CAP + 2) / 2 - ((nwords + 3) & ~3)) / 2);
   for (int it = w; it < nch * (CH / 128); it += NW) {
     const int c = it / (CH / 128);
     const int j1 = surfCnt[c0 + c];
@@ -1449,9 +1454,15 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
     for (int k = 0; k < 4; k++) q[k] = (j + 32 * k < j1) ? src[j + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      if (j + 32 * k < j1) {
-        const int sl = slot_of(q[k].x, q[k].y, q[k].z);
-        if (sl >= 0) atomicAdd(&cnts[sl >> 1], (sl & 1) ? 65536u : 1u);
+      int sl = -1;
+      if (j + 32 * k < j1) sl = slot_of(q[k].x, q[k].y, q[k].z);
+      if (sl >= 0) atomicAdd(&cnts[sl >> 1], (sl & 1) ? 65536u : 1u);
+      const unsigned hm = __ballot_sync(FE_FULL, sl >= 0);
+      if (hm) {
+        int at = 0;
+        if (lane == __ffs(hm) - 1) at = atomicAdd(&s_hl, __popc(hm));
+        at = __shfl_sync(FE_FULL, at, __ffs(hm) - 1) + __popc(hm & lanemask_lt());
+        if (sl >= 0 && at < hlCap) { hlist[2 * at] = (unsigned)(c * CH + j + 32 * k); hlist[2 * at + 1] = (unsigned)sl; }
       }
     }
   }
@@ -1496,6 +1507,16 @@ __global__ void __launch_bounds__(NTS) k_surface_grid_cells(
   // (4) scatter: the start of a slot doubles as its cursor (it ends at the slot's end <= n <= 65535, so a
   //     16-bit half never carries into its neighbour); the order inside a slot is free
   float4* so = sorted + base;
+  if (s_hl <= hlCap) {  // every halo point is listed
+    const int nl = s_hl;
+    for (int e = tid; e < nl; e += NTS) {
+      const unsigned sl = hlist[2 * e + 1];
+      const float4 q = surf[base + hlist[2 * e]];
+      const unsigned old = atomicAdd(&cnts[sl >> 1], (sl & 1) ? 65536u : 1u);
+      so[(sl & 1) ? (int)(old >> 16) : (int)(old & 0xFFFFu)] = q;
+    }
+    return;
+  }
   for (int it = w; it < nch * (CH / 128); it += NW) {
     const int c = it / (CH / 128);
     const int j1 = surfCnt[c0 + c];
