@@ -651,7 +651,11 @@ __device__ void cluster_extract(ClusterSm& S, int E, float tol_f, float r2f, int
     }
     __syncthreads();
     // ---- flatten; label every component with its smallest entry (= its first point in the cloud) ----
-    for (int p = tid; p < E; p += NT) parentS[p] = uf_find_readonly(parentS, (unsigned)p);
+    // (two steps through S.aux — the unit indices are no longer needed — so that no thread rewrites a link
+    // while another one is still walking it)
+    for (int p = tid; p < E; p += NT) S.aux[p] = (unsigned short)uf_find_readonly(parentS, (unsigned)p);
+    __syncthreads();
+    for (int p = tid; p < E; p += NT) parentS[p] = (unsigned)S.aux[p];
     __syncthreads();
     unsigned* minE = kS;
     for (int p = tid; p < E; p += NT) minE[p] = 0xFFFFFFFFu;

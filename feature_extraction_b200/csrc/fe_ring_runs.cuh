@@ -58,14 +58,11 @@ __device__ __forceinline__ unsigned ring_mask_of(unsigned cd, int single_ring) {
   return (1u << r) | ((cd & 16u) ? (1u << (r + 1)) : 0u);
 }
 
-__device__ __forceinline__ unsigned rr_find(unsigned short* parent, unsigned x) {
+// Every lane of the warp walks the same chain (read-only: links are only ever written by lane 0 between
+// __syncwarp()s, and a root is the smallest run of its set, so chains are short).
+__device__ __forceinline__ unsigned rr_find(const unsigned short* parent, unsigned x) {
   unsigned p = parent[x];
-  while (p != x) {
-    const unsigned gp = parent[p];
-    parent[x] = (unsigned short)gp;  // path halving; every lane of the warp writes the same values
-    x = p;
-    p = gp;
-  }
+  while (p != x) { x = p; p = parent[x]; }
   return x;
 }
 
@@ -152,6 +149,7 @@ __device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const D
     }
     R += __popc(hm);
     cx = __shfl_sync(FE_FULL, q.x, 31); cy = __shfl_sync(FE_FULL, q.y, 31); cz = __shfl_sync(FE_FULL, q.z, 31);
+    __syncwarp();  // the run records written here are read (lane 0 extends a run) in the next round
   }
   if (lane == 0) B.start[R] = n;
   __syncwarp();
@@ -211,7 +209,7 @@ __device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const D
     nC += __popc(km);
   }
   __syncwarp();
-  if (nC == 0) return true;
+  if (nC == 0) return true;  // (all lanes are past their last read of the run buffer: the __syncwarp above)
   // ---- PCL's final std::sort(rbegin, rend, size<) ----
   if (nC > 1 && lane == 0) {
     const int* cs = B.csize;
@@ -316,6 +314,7 @@ __device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const D
     }
     doneOk += __popc(om);
   }
+  __syncwarp();  // the next ring reuses the run buffer
   return true;
 }
 
