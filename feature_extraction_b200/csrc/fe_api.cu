@@ -60,6 +60,7 @@ struct Slot {
   unsigned char* d_gridHdr = nullptr;  // per-scan index of the halo cell grid (bit map, word prefix, slot table)
   int* d_tabOk = nullptr;
   int64_t capGridHdr = 0;
+  int *d_ringBase = nullptr, *d_ovfRuns = nullptr, *d_scanFlag = nullptr;  // K2: ring segment offsets per scan, rings for the wide run kernel
   int *d_ovfRings = nullptr, *d_ovfRings2 = nullptr, *d_ovfMerge = nullptr, *d_ovfMerge2 = nullptr, *d_ovfSurf = nullptr;
   unsigned char* d_slabs = nullptr;
   int64_t capRowStart = 0;
@@ -266,7 +267,7 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_ringPts, s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_gridHdr, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_perScan2, s.d_outOff2, s.d_gather2};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_gridHdr, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_ringBase, s.d_ovfRuns, s.d_scanFlag, s.d_perScan2, s.d_outOff2, s.d_gather2};
   for (void* p : dv) if (p) cudaFree(p);
   void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
   for (void* p : hv) if (p) cudaFreeHost(p);
@@ -316,6 +317,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_kpNbrOff, (size_t)s.capKp)); CK(dalloc(&s.d_kpRank, (size_t)s.capKp));
   CK(dalloc(&s.d_kpListM, (size_t)s.capKp)); CK(dalloc(&s.d_kpListL, (size_t)s.capKp));
   CK(dalloc(&s.d_surfN, ns)); CK(dalloc(&s.d_perScan, ns)); CK(dalloc(&s.d_outOff, ns + 1)); CK(dalloc(&s.d_tabOk, ns));
+  CK(dalloc(&s.d_ringBase, ns * 17)); CK(dalloc(&s.d_ovfRuns, ns * 16)); CK(dalloc(&s.d_scanFlag, ns));
   CK(dalloc(&s.d_ovfRings, ns)); CK(dalloc(&s.d_ovfRings2, ns)); CK(dalloc(&s.d_ovfMerge, ns)); CK(dalloc(&s.d_ovfMerge2, ns));
   CK(dalloc(&s.d_ovfSurf, ns));
   CK(dalloc(&s.d_slabs, (size_t)NGLOBAL * cluster_slab_bytes(ECAP_G)));
@@ -441,7 +443,8 @@ const size_t kClusterSmemM = cluster_smem_bytes(ECAP_M, NTM);
 
 int set_kernel_attrs(fe_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_ring_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingRunsSm)));
+  CK(cudaFuncSetAttribute(k_ring_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingRunsSmT<RW>)));
+  CK(cudaFuncSetAttribute(k_ring_runs_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NW_RR * sizeof(RunBufT<RW2>))));
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NTL, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL2));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_L, NT2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL));
@@ -576,9 +579,16 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
   if (ctx->gridClustering)
     k_cluster_rings<ECAP, NTF, 4, false><<<nscans, NTF, kClusterSmem, s.stream>>>(FE_K2_ARGS, nullptr, nullptr, s.d_ovfRings, ovfR, nullptr);
   else
-    k_ring_runs<<<nscans, NT_RR, sizeof(RingRunsSm), s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr,
-                                                                 s.d_ringPts, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC,
-                                                                 s.d_ctr, s.d_ovfRings, ovfR);
+  {
+    k_ring_runs<<<nscans, NT_RR, sizeof(RingRunsSmT<RW>), s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr,
+                                                                      s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
+                                                                      s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag,
+                                                                      s.d_ovfRings, ovfR);
+    k_ring_runs_wide<<<std::min(nscans * 4, ctx->numSms * 7), NT_RR, NW_RR * sizeof(RunBufT<RW2>), s.stream>>>(
+        s.d_scan_off, P, s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC, s.d_ctr,
+        s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag, s.d_ovfRings, ovfR);
+    ctx->launches++;
+  }
   k_cluster_rings<ECAP_L, NTL, 1, false><<<gridL, NTL, kClusterSmemL2, s.stream>>>(FE_K2_ARGS, s.d_ovfRings, ovfR, s.d_ovfRings2, ovfR2, nullptr);
   k_cluster_rings<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K2_ARGS, s.d_ovfRings2, ovfR2, nullptr, nullptr, s.d_slabs);
 #undef FE_K2_ARGS

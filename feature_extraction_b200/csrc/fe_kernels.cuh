@@ -93,7 +93,7 @@ struct DevCounters {
   int ovf_surf;    // scans deferred from the shared-memory K4a to the global-memory one
   int desc_unordered;  // keypoints with more than DCAP_L contributions (summed with atomics, not in PCL's order)
   int ovf_merge2;      // scans deferred from the large K3 to the global-memory instantiation
-  int pad[1];
+  int ovf_runs;        // scans the first run-based K2 kernel hands to the wide one (a ring with more than RW runs)
   unsigned long long nbr_cursor;  // neighbour-list pool (K4b -> K4d)
   int kd_cursor;                  // next keypoint batch of the fast K4d instantiation
   int kw_cursor;                  // next keypoint of the warp-per-keypoint K4d

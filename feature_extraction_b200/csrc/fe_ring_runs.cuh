@@ -24,24 +24,28 @@ namespace fe {
 
 constexpr int NT_RR = 128;       // threads per scan block (4 warps)
 constexpr int NW_RR = NT_RR / 32;
-constexpr int RW = 256;          // runs of one ring a warp keeps in shared memory
+constexpr int RW = 128;          // runs of one ring a warp of the first kernel keeps in shared memory (7 KB per warp: 12+ blocks / SM)
+constexpr int RW2 = 256;         // ... of the second kernel, which takes the scans with a ring beyond RW (hundreds of poles in one ring)
 
-struct RunBuf {                  // one per warp
-  float minx[RW], maxx[RW], miny[RW], maxy[RW];  // xy box of every run
-  int start[RW + 1];             // first entry of every run (start[R] = n)
-  int csize[RW];                 // at a root: entries of the component
-  unsigned short parent[RW];     // union-find over runs, root = smallest run
-  unsigned short list[RW];       // kept clusters (root runs) in output order
+template <int RWT>
+struct RunBufT {                 // one per warp, shared memory
+  float minx[RWT], maxx[RWT], miny[RWT], maxy[RWT];  // xy box of every run
+  int start[RWT + 1];            // first entry of every run (start[R] = n)
+  int csize[RWT];                // at a root: entries of the component
+  unsigned short parent[RWT];    // union-find over runs, root = smallest run
+  unsigned short list[RWT];      // kept clusters (root runs) in output order
+  static constexpr int cap = RWT;
 };
 
-struct RingRunsSm {
+template <int RWT>
+struct RingRunsSmT {
   int pre[MAXCHUNK + 1];
   int sc[40];
   int cnt[NW_RR][17];            // phase A: entries per (warp, ring); [16] = entries in no ring
   int ringBase[18];
   int nextRing;
   int defer;
-  RunBuf rb[NW_RR];
+  RunBufT<RWT> rb[NW_RR];
 };
 
 __device__ __forceinline__ int f2ord(float f) {  // monotone float -> int
@@ -67,7 +71,8 @@ __device__ __forceinline__ unsigned rr_find(const unsigned short* parent, unsign
 }
 
 // Is any entry of run a within the tolerance of any entry of run b?  Warp-uniform.
-__device__ bool rr_runs_linked(const RunBuf& B, const float4* P, int a, int b, float r2f, float r2box) {
+template <class RB>
+__device__ bool rr_runs_linked(const RB& B, const float4* P, int a, int b, float r2f, float r2box) {
   const int lane = threadIdx.x & 31;
   int big = a, small = b;
   if (B.start[b + 1] - B.start[b] > B.start[a + 1] - B.start[a]) { big = b; small = a; }
@@ -103,9 +108,10 @@ __device__ bool rr_runs_linked(const RunBuf& B, const float4* P, int a, int b, f
 }
 
 // (P is the block's own scratch, written in phase A of the same kernel: plain pointers, no read-only path.)
-// One ring: entries P[0, n) in original order.  Returns false when the ring has more than RW runs
-// (nothing has been written then).  Warp-uniform; all 32 lanes call.
-__device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const DevParams& Pm,
+// One ring: entries P[0, n) in original order.  Returns false when the ring has more runs than the buffer
+// holds (nothing has been written then).  Warp-uniform; all 32 lanes call.
+template <class RB>
+__device__ bool rr_cluster_ring(RB& B, const float4* P, const int n, const DevParams& Pm,
                                 float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBaseOut, int* __restrict__ kfCntOut,
                                 float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBaseOut, int* __restrict__ kcCntOut,
                                 DevCounters* __restrict__ ctr) {
@@ -127,7 +133,7 @@ __device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const D
     const bool head = valid && (e == 0 || !(l2_simple(ux, uy, uz, q.x, q.y, q.z) < r2f));
     const unsigned hm = __ballot_sync(FE_FULL, head);
     const int nv = min(32, n - e0);
-    if (R + __popc(hm) > RW) return false;
+    if (R + __popc(hm) > B.cap) return false;
     if (valid) {
       const unsigned below = hm & le;                      // heads at or below this lane
       const int segStart = below ? 31 - __clz(below) : 0;  // none: the run continues from the previous 32
@@ -185,21 +191,16 @@ __device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const D
     }
   }
   __syncwarp();
-  // ---- flatten; clusters that pass the size gate in discovery order (ascending root) ----
-  {
-    unsigned short rt[RW / 32];
-#pragma unroll
-    for (int k = 0; k < RW / 32; k++) {
-      const int r = k * 32 + lane;
-      unsigned x = (unsigned)r;
-      if (r < R) { unsigned p = B.parent[x]; while (p != x) { x = p; p = B.parent[x]; } }
-      rt[k] = (unsigned short)x;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < RW / 32; k++) { const int r = k * 32 + lane; if (r < R) B.parent[r] = rt[k]; }
-    __syncwarp();
+  // ---- flatten (through `list`, free until the clusters are listed); clusters that pass the size gate in
+  //      discovery order (ascending root) ----
+  for (int r = lane; r < R; r += 32) {
+    unsigned x = (unsigned)r, p = B.parent[x];
+    while (p != x) { x = p; p = B.parent[x]; }
+    B.list[r] = (unsigned short)x;
   }
+  __syncwarp();
+  for (int r = lane; r < R; r += 32) B.parent[r] = B.list[r];
+  __syncwarp();
   int nC = 0;
   for (int r0 = 0; r0 < R; r0 += 32) {
     const int r = r0 + lane;
@@ -213,7 +214,8 @@ __device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const D
   // ---- PCL's final std::sort(rbegin, rend, size<) ----
   if (nC > 1 && lane == 0) {
     const int* cs = B.csize;
-    pcl_cluster_order(B.list, nC, [=](unsigned short id) { return cs[id]; });
+    unsigned short* lst = B.list;
+    pcl_cluster_order(lst, nC, [=](unsigned short id) { return cs[id]; });
   }
   __syncwarp();
   // ---- getCylinderSegments gate (src:282-325): xy box diagonal of the cluster, strict < 2*threshold ----
@@ -318,22 +320,47 @@ __device__ bool rr_cluster_ring(RunBuf& B, const float4* P, const int n, const D
   return true;
 }
 
-// One block per scan (scanList == nullptr) — every scan; scans that cannot be handled here (a ring with
-// more than RW runs, more ring entries than the scan's scratch slot) are appended to ovfList for the
-// grid-based kernels.
-__global__ void __launch_bounds__(NT_RR) k_ring_runs(
+// Phase B for one scan whose ring segments [ringBase[r], ringBase[r+1]) are in place at RP: the warps take rings
+// off the block's counter.  A ring with more runs than a warp's buffer holds is listed for the wide kernel (its
+// outputs are untouched); the other rings of the scan are finished here.
+template <int RWT>
+__device__ void rr_scan_rings(RingRunsSmT<RWT>& S, const int s, const float4* RP, const int nRings, const DevParams& P,
+                              float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
+                              float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
+                              DevCounters* __restrict__ ctr, int* __restrict__ ovfRuns, int* __restrict__ ovfRunsCount) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  RunBufT<RWT>& B = S.rb[w];
+  for (;;) {
+    int ring = 0;
+    if (lane == 0) ring = atomicAdd(&S.nextRing, 1);
+    ring = __shfl_sync(FE_FULL, ring, 0);
+    if (ring >= nRings) break;
+    const int r0 = S.ringBase[ring], n = S.ringBase[ring + 1] - r0;
+    if (n == 0) continue;
+    const bool done = rr_cluster_ring(B, RP + r0, n, P, kfPool, kfCap, &kfBase[s * 16 + ring], &kfCnt[s * 16 + ring], kcPool, kcCap,
+                                      kcBase ? &kcBase[s * 16 + ring] : nullptr, kcBase ? &kcCnt[s * 16 + ring] : nullptr, ctr);
+    if (!done && lane == 0) ovfRuns[atomicAdd(ovfRunsCount, 1)] = s * 16 + ring;
+  }
+}
+
+// First kernel: one block per scan, every scan.  A ring of more than RW runs is handed to the second kernel (the
+// ring segments and their offsets stay in global memory, so nothing is bucketed twice); a scan with more ring
+// entries than its scratch slot goes straight to the grid-based kernels.
+__global__ void __launch_bounds__(NT_RR, 12) k_ring_runs(
     const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta, const int* __restrict__ cropCnt,
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P, int single_ring,
-    float4* ringPts, float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
+    float4* ringPts, int* __restrict__ ringBaseOut, float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
     float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
-    DevCounters* __restrict__ ctr, int* __restrict__ ovfList, int* __restrict__ ovfCount) {
+    DevCounters* __restrict__ ctr, int* __restrict__ ovfRuns, int* __restrict__ ovfRunsCount, int* __restrict__ scanFlag,
+    int* __restrict__ ovfList, int* __restrict__ ovfCount) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RingRunsSm& S = *reinterpret_cast<RingRunsSm*>(smem_raw);
+  RingRunsSmT<RW>& S = *reinterpret_cast<RingRunsSmT<RW>*>(smem_raw);
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const long long base = scan_off[s];
   const int nScan = (int)(scan_off[s + 1] - base);
   const int nch = chunk_off[s + 1] - chunk_off[s];
   if (tid < 16) { kfBase[s * 16 + tid] = 0; kfCnt[s * 16 + tid] = 0; if (kcBase) { kcBase[s * 16 + tid] = 0; kcCnt[s * 16 + tid] = 0; } }
+  if (tid == 0) scanFlag[s] = 0;  // the wide kernel sets it when it sends the scan on to the grid-based kernels
   if (nch > MAXCHUNK) { if (tid == 0) atomicOr(&ctr->err, ERR_CHUNKS); return; }
   if (tid < NW_RR * 17) (&S.cnt[0][0])[tid] = 0;
   if (tid == 0) { S.nextRing = 0; S.defer = 0; }
@@ -415,20 +442,29 @@ __global__ void __launch_bounds__(NT_RR) k_ring_runs(
   }
   __syncthreads();  // the block's global writes are visible to all its threads from here on
   // ---- phase B: a warp per ring, rings handed out dynamically ----
-  RunBuf& B = S.rb[w];
-  for (;;) {
-    int ring = 0;
-    if (lane == 0) ring = atomicAdd(&S.nextRing, 1);
-    ring = __shfl_sync(FE_FULL, ring, 0);
-    if (ring >= nRings) break;
-    const int r0 = S.ringBase[ring], n = S.ringBase[ring + 1] - r0;
-    if (n == 0) continue;
-    const bool done = rr_cluster_ring(B, RP + r0, n, P, kfPool, kfCap, &kfBase[s * 16 + ring], &kfCnt[s * 16 + ring], kcPool, kcCap,
-                                      kcBase ? &kcBase[s * 16 + ring] : nullptr, kcBase ? &kcCnt[s * 16 + ring] : nullptr, ctr);
-    if (!done) {  // more runs than the buffer holds (unordered input, clutter): the grid-based kernels redo the scan
-      if (lane == 0 && atomicExch(&S.defer, 1) == 0) ovfList[atomicAdd(ovfCount, 1)] = s;
-      break;
-    }
+  if (tid < 17) ringBaseOut[s * 17 + tid] = S.ringBase[tid];  // for the wide kernel, should a ring of this scan need it
+  rr_scan_rings<RW>(S, s, RP, nRings, P, kfPool, kfCap, kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfRuns, ovfRunsCount);
+}
+
+// Second kernel: the rings the first one listed (hundreds of poles in one ring), a warp per ring with RW2 runs;
+// what exceeds that — entries in arbitrary order, mostly — sends the ring's whole scan to the grid-based kernels.
+__global__ void __launch_bounds__(NT_RR) k_ring_runs_wide(
+    const long long* __restrict__ scan_off, DevParams P, const float4* ringPts, const int* __restrict__ ringBaseIn,
+    float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
+    float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
+    DevCounters* __restrict__ ctr, const int* __restrict__ ringList, const int* __restrict__ nList, int* __restrict__ scanFlag,
+    int* __restrict__ ovfList, int* __restrict__ ovfCount) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RunBufT<RW2>* bufs = reinterpret_cast<RunBufT<RW2>*>(smem_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  RunBufT<RW2>& B = bufs[w];
+  const int nl = *nList;
+  for (int li = blockIdx.x * NW_RR + w; li < nl; li += gridDim.x * NW_RR) {
+    const int id = ringList[li], s = id >> 4, ring = id & 15;
+    const int r0 = ringBaseIn[s * 17 + ring], n = ringBaseIn[s * 17 + ring + 1] - r0;
+    const bool done = rr_cluster_ring(B, ringPts + scan_off[s] + r0, n, P, kfPool, kfCap, &kfBase[s * 16 + ring], &kfCnt[s * 16 + ring],
+                                      kcPool, kcCap, kcBase ? &kcBase[s * 16 + ring] : nullptr, kcBase ? &kcCnt[s * 16 + ring] : nullptr, ctr);
+    if (!done && lane == 0 && atomicExch(&scanFlag[s], 1) == 0) ovfList[atomicAdd(ovfCount, 1)] = s;
   }
 }
 

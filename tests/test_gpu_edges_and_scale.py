@@ -304,3 +304,39 @@ def test_very_large_scan_takes_the_deferred_paths(ob, synth):
     assert bits_equal(kp, r["keypoints"])
     assert check_descriptors(d, r["descriptors"])[1] == 0
     nd.close()
+
+
+def test_bbox_sentinels_and_extreme_size_gates_follow_the_reference(ob, node):
+    """src:289-290 initialises the cluster box with +-1000: a cluster beyond 1000 m keeps the sentinel as
+    one of its bounds and fails the diameter gate; a cluster straddling nothing special passes.  Also the
+    size gate at its extremes (min 1: single returns are clusters; max smaller than a wall run)."""
+    from feature_extraction_b200 import FeatureExtractionNode
+    P = ob.node_default()
+    P.x_min, P.x_max, P.y_min, P.y_max = -2000.0, 2000.0, -2000.0, 2000.0
+    P.cluster_min_count, P.cluster_max_count = 1, 6
+    rng = np.random.default_rng(21)
+    pts = []
+    # every cluster sits a little below the sensor plane, so its elevation is in ring 7's window [-2, 0] at any range
+    for cx, cy in ((1500.0, 3.0), (-1500.0, -7.0), (30.0, 1200.0), (12.0, -1100.0), (999.95, 0.0), (1000.02, 40.0), (20.0, 4.0), (25.0, -3.0)):
+        for k in range(4):
+            pts.append((cx + 0.03 * k, cy + 0.01 * rng.normal(), -0.3 - 0.01 * k, 0.0))
+    for k in range(9):                      # a run of 9 returns: above max_count, dropped whole
+        pts.append((40.0 + 0.2 * k, 10.0, -0.4, 0.0))
+    pts.append((55.0, -20.0, -0.5, 0.0))    # a single return: a cluster of its own (min 1)
+    pts = np.array(pts, np.float32)
+    offs = np.array([0, len(pts)], np.int64)
+    rp = np.zeros((1, 2))
+    nd = FeatureExtractionNode(to_fe_params(P), max_points=1 << 16, max_scans=4, max_keypoints=1024)
+    nd.enableCloudOutputs(True)
+    ko, kp, d = nd.processBatch(pts, offs, rp)
+    co, cloud, kco, kcloud = nd.cloudOutputs(1)
+    nd.close()
+    r = ob.process_scan(P, pts, 0.0, 0.0, mode=0)
+    assert bits_equal(kp, r["keypoints"]) and bits_equal(kcloud, r["keypoint_cloud"]) and bits_equal(cloud, r["cloud"])
+    assert check_descriptors(d, r["descriptors"])[1] == 0
+    xs, ys = r["keypoints"][:, 0], r["keypoints"][:, 1]
+    assert len(r["cloud"]) == len(pts)
+    assert not np.any(np.abs(xs) > 1400.0) and not np.any(np.abs(ys) > 1000.0)   # far clusters keep a sentinel bound: gate fails
+    assert np.any(np.abs(xs - 1000.065) < 0.01)      # ... except just beyond 1000 m, where min x = 1000 still gives a small box
+    assert np.any(np.abs(xs - 55.0) < 1e-3)          # the single return made it through
+    assert not np.any(np.abs(xs - 40.8) < 1.0)       # the oversize run did not
