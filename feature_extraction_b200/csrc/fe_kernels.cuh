@@ -2261,7 +2261,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
 // the records by key = bin | d2 | index with a bitonic network in its own slice of shared memory, sums
 // every bin's run in that order (PCL's order, bit-identical) and writes the 1980-float row as zeros plus
 // the few non-zero bins.
-constexpr int DW_CAP = 512;     // neighbours per keypoint of the warp kernel
+constexpr int DW_CAP = 256;     // neighbours per keypoint of the warp kernel
 constexpr int DW_WARPS = 8;
 constexpr size_t desc_warp_smem_bytes() { return (size_t)DW_WARPS * DW_CAP * 12; }
 
