@@ -72,6 +72,7 @@ struct Slot {
   // pinned host mirrors
   long long* h_scan_off = nullptr;
   int* h_chunk_off = nullptr;
+  int4 *h_chunkTab = nullptr, *d_chunkTab = nullptr;  // per chunk: scan, (chunk of scan << 12) | points, first point lo, hi
   float* h_rot = nullptr;
   DevCounters* h_ctr = nullptr;
   int* h_kpOff = nullptr;
@@ -267,9 +268,9 @@ void free_slot(Slot& s) {
   void* dv[] = {s.d_ringPts, s.d_pts, s.d_surf, s.d_crop, s.d_sorted, s.d_full, s.d_cropMeta, s.d_keyA, s.d_keyB, s.d_valA, s.d_valB,
                 s.d_sortedKey, s.d_rho, s.d_scan_off, s.d_chunk_off, s.d_surfCnt, s.d_cropCnt, s.d_rot, s.d_kfBase,
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
-                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_gridHdr, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_ringBase, s.d_ovfRuns, s.d_scanFlag, s.d_perScan2, s.d_outOff2, s.d_gather2};
+                s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_gridHdr, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_ringBase, s.d_ovfRuns, s.d_scanFlag, s.d_perScan2, s.d_outOff2, s.d_gather2, s.d_chunkTab};
   for (void* p : dv) if (p) cudaFree(p);
-  void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
+  void* hv[] = {s.h_chunkTab, s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
   for (void* p : hv) if (p) cudaFreeHost(p);
   for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
   for (GraphEntry& g : s.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -309,6 +310,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_rho, np));
   CK(dalloc(&s.d_scan_off, ns + 1)); CK(dalloc(&s.d_chunk_off, ns + 1));
   CK(dalloc(&s.d_surfCnt, (size_t)s.capChunks)); CK(dalloc(&s.d_cropCnt, (size_t)s.capChunks));
+  CK(dalloc(&s.d_chunkTab, (size_t)s.capChunks)); CK(halloc(&s.h_chunkTab, (size_t)s.capChunks));
   CK(dalloc(&s.d_rot, ns * 9));
   CK(dalloc(&s.d_kfBase, ns * 16)); CK(dalloc(&s.d_kfCnt, ns * 16));
   CK(dalloc(&s.d_kcBase, ns * 16)); CK(dalloc(&s.d_kcCnt, ns * 16));
@@ -359,6 +361,8 @@ std::string err_bits(int e) {
 int stage_scans_copy(fe_ctx* ctx, Slot& s, int nscans, bool deferRot) {
   CK(cudaMemcpyAsync(s.d_scan_off, s.h_scan_off, (nscans + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_chunk_off, s.h_chunk_off, (nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+  const int nch = s.h_chunk_off[nscans];
+  if (nch > 0) CK(cudaMemcpyAsync(s.d_chunkTab, s.h_chunkTab, (size_t)nch * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
   if (!deferRot) CK(cudaMemcpyAsync(s.d_rot, s.h_rot, (size_t)nscans * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
   return FE_OK;
 }
@@ -378,7 +382,14 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
     s.maxScanPts = std::max(s.maxScanPts, n);
     s.h_scan_off[i] = (long long)(offs[i] - o0);
     s.h_chunk_off[i] = nch;
-    nch += (int)((n + CH - 1) / CH);
+    const int64_t nc = (n + CH - 1) / CH;
+    if (nc > (int64_t)s.capChunks - nch) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds the chunk capacity");
+    for (int64_t c = 0; c < nc; c++) {  // K1's chunk table (k_level_crop_ring)
+      const int64_t b = offs[i] - o0 + c * CH;
+      s.h_chunkTab[nch + c] = make_int4(i, (int)(((unsigned)c << 12) | (unsigned)std::min<int64_t>(CH, n - c * CH)),
+                                        (int)(unsigned)(b & 0xFFFFFFFFll), (int)(b >> 32));
+    }
+    nch += (int)nc;
     if (deferRot) continue;  // enqueue_pipeline computes the matrices range by range (lateRp)
     if (rp) leveling_matrix(rp[2 * i], rp[2 * i + 1], s.h_rot + 9 * i);
     else { float* m = s.h_rot + 9 * i; for (int k = 0; k < 9; k++) m[k] = (k % 4 == 0) ? 1.0f : 0.0f; }
@@ -655,10 +666,10 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
       const int ca = s.h_chunk_off[a], cb = s.h_chunk_off[b];
       if (cb <= ca) continue;
       if (lay.raw)
-        k_level_crop_ring<true, true><<<cb - ca, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+        k_level_crop_ring<true, true><<<cb - ca, 256, 0, s.stream>>>(d_pts, s.d_chunkTab, s.d_rot, P, k1flags,
                                                                s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay, ca);
       else
-        k_level_crop_ring<false, true><<<cb - ca, 256, 0, s.stream>>>(d_pts, s.d_scan_off, s.d_chunk_off, nscans, s.d_rot, P, k1flags,
+        k_level_crop_ring<false, true><<<cb - ca, 256, 0, s.stream>>>(d_pts, s.d_chunkTab, s.d_rot, P, k1flags,
                                                                 s.d_surf, s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, lay, ca);
       ctx->launches++;
       if (lateRp && part + 1 < nparts) mark(ctx, s, "K1 level+crop+ring");
@@ -1339,7 +1350,7 @@ static int stage_k1(fe_ctx* ctx, fe_point_t* cloud, int64_t n, double roll, doub
   st = stage_scans(ctx, s, offs, rp, 1, &npts, &nch);
   if (st) return st;
   CK(cudaMemcpyAsync(s.d_pts, cloud, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
-  k_level_crop_ring<false, false><<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+  k_level_crop_ring<false, false><<<nch, 256, 0, s.stream>>>(s.d_pts, s.d_chunkTab, s.d_rot, ctx->dp, flags, s.d_surf,
                                                s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_full, RawLayout{nullptr, 0, 0, 0, 0}, 0);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -1374,7 +1385,7 @@ static int stage_upload_k1(fe_ctx* ctx, Slot& s, const fe_point_t* in, int64_t n
   if (st) return st;
   if (n > 0) CK(cudaMemcpyAsync(s.d_pts, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s.stream));
   if (*nchOut > 0) {
-    k_level_crop_ring<false, false><<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_scan_off, s.d_chunk_off, 1, s.d_rot, ctx->dp, flags, s.d_surf,
+    k_level_crop_ring<false, false><<<*nchOut, 256, 0, s.stream>>>(s.d_pts, s.d_chunkTab, s.d_rot, ctx->dp, flags, s.d_surf,
                                                      s.d_surfCnt, s.d_crop, s.d_cropMeta, s.d_cropCnt, nullptr, RawLayout{nullptr, 0, 0, 0, 0}, 0);
     ctx->launches++;
   }

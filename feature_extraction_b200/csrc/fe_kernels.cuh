@@ -168,14 +168,12 @@ struct RawLayout {  // records of fe_point_layout_t; raw == nullptr: the input i
 // ============================================================================================
 template <bool RAW, bool FUSED>
 __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
-    const float4* __restrict__ pts, const long long* __restrict__ scan_off,
-    const int* __restrict__ chunk_off, int n_scans, const float* __restrict__ rot, DevParams P,
+    const float4* __restrict__ pts, const int4* __restrict__ chunkTab, const float* __restrict__ rot, DevParams P,
     int flags_rt, float4* __restrict__ surf, int* __restrict__ surfCnt, float4* __restrict__ crop,
     unsigned* __restrict__ cropMeta, int* __restrict__ cropCnt, float4* __restrict__ full_out,
     RawLayout L, int chunk_base) {
   // FUSED: the cloudCallback path, every stage on (surface stream optional); otherwise run-time flags
   const int flags = FUSED ? (F_ELEV | F_ROT | F_CROP | F_RING | (flags_rt & F_SURF)) : flags_rt;
-  __shared__ int s_scan;
   __shared__ int s_ws[8], s_wc[8];
   // One tile of shared memory holds the chunk twice over: first its input points, brought in by a single
   // TMA bulk copy (float4 input), then — slot by slot, each written by the thread that read it — the
@@ -184,30 +182,24 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
   __shared__ __align__(8) unsigned long long s_bar;
   const int chunk = chunk_base + blockIdx.x;  // a batch may be launched in several chunk ranges
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) {
-    int lo = 0, hi = n_scans - 1;  // largest s with chunk_off[s] <= chunk
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (chunk_off[mid] <= chunk) lo = mid; else hi = mid - 1;
-    }
-    s_scan = lo;
-    if (!RAW) {
-      const long long b0 = scan_off[lo] + (long long)(chunk - chunk_off[lo]) * CH;
-      const int n0 = (int)min((long long)CH, scan_off[lo + 1] - b0);
-      mbar_init(&s_bar, 1);
-      mbar_expect_tx(&s_bar, (unsigned)n0 * 16u);
-      tma_load_1d(s_o, pts + b0, (unsigned)n0 * 16u, &s_bar);
-    }
+  // chunk -> (scan, chunk of the scan, points, first point), tabulated by the host while it stages the
+  // offsets: ONE load stands between the start of the block and its bulk copy (a bisection of chunk_off
+  // followed by the scan_off reads was ~15 dependent loads, a sixth of the block's life)
+  const int4 ct = __ldg(chunkTab + chunk);
+  const int s = ct.x;
+  const int c = (int)((unsigned)ct.y >> 12);
+  const int nIn = ct.y & 4095;
+  const long long base = (long long)(((unsigned long long)(unsigned)ct.w << 32) | (unsigned)ct.z);
+  if (!RAW && tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_expect_tx(&s_bar, (unsigned)nIn * 16u);
+    tma_load_1d(s_o, pts + base, (unsigned)nIn * 16u, &s_bar);
   }
-  __syncthreads();
-  const int s = s_scan;
-  const int c = chunk - chunk_off[s];
-  const long long base = scan_off[s] + (long long)c * CH;
-  const int nIn = (int)min((long long)CH, scan_off[s + 1] - base);
-  if (!RAW) mbar_wait(&s_bar, 0);
   float m[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) m[i] = (flags & F_ROT) ? rot[s * 9 + i] : 0.0f;
+  __syncthreads();
+  if (!RAW) mbar_wait(&s_bar, 0);
 
   unsigned code = 0;             // 8 x 4 bits: ring id of round r (first ring containing el)
   unsigned fl = 0;               // bit r: surf, bit 8+r: crop, bit 16+r: dual ring, bit 24+r: no ring
@@ -251,13 +243,16 @@ __global__ void __launch_bounds__(256, 6) k_level_crop_ring(
           // ring i keeps (i-7)*2-1 +- 1 inclusive (src:200-202); windows share their end points
           rm = 0u;
           if (isfinite(el)) {
-            const int i0 = (int)floorf(fminf(fmaxf((el + 16.0f) * 0.5f, -2.0f), 18.0f));
-#pragma unroll
-            for (int d = -1; d <= 1; d++) {
-              const int i = i0 + d;
-              const float lo = (float)(2 * i - 16), hi = (float)(2 * i - 14);
-              if (i >= 0 && i < 16 && !(el < lo || el > hi)) rm |= 1u << i;
-            }
+            // i = the ring with lo <= el < lo + 2 (lo = 2i - 16).  The float (el + 16) / 2 can round across
+            // an integer, so its floor is off by at most one: one correction step.  An angle exactly on a
+            // window's lower end is also the upper end of ring i - 1.  (Far outside angles end at i <= -3
+            // or i >= 19 through the clamp: no ring.)
+            int i = (int)floorf(fminf(fmaxf((el + 16.0f) * 0.5f, -2.0f), 18.0f));
+            float lo = (float)(2 * i - 16);
+            if (el < lo) { i--; lo -= 2.0f; }
+            else if (el >= lo + 2.0f) { i++; lo += 2.0f; }
+            if (i >= 0 && i < 16) rm = 1u << i;
+            if (el == lo && i >= 1 && i <= 16) rm |= 1u << (i - 1);
           }
         }
         if (rm == 0u) fl |= 1u << (24 + r);

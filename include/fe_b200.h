@@ -207,13 +207,13 @@ int fe_timer_end(fe_ctx_t* ctx, float* elapsed_ms);
 /* Work counters of the last fe_process_batch_device call (for roofline arithmetic):
  * out[0..9] = points, surface points kept, cropped points, ring clusters (keypoints_full),
  * keypoints, sum of 3DSC neighbours, scans deferred to the large K2, to the large K3, to the
- * global-memory K4a, keypoints whose descriptor was summed out of PCL's order (> 8192 contributions). */
+ * global-memory K4a, keypoints whose descriptor was summed out of PCL's order (a single bin with
+ * more than 8192 contributions; larger neighbourhoods are otherwise handled exactly, in bin groups). */
 int fe_get_batch_stats(fe_ctx_t* ctx, int64_t out[10]);
 
 /* Per-kernel CUDA-event times (ms) of the last device call; names are static strings.  Only collected
- * after fe_enable_stage_timing(ctx, 1), which also makes the stages run strictly one after the other
- * (by default the surface-grid kernel runs on a side stream next to the clustering kernels, so an
- * event pair around one of them would time both). */
+ * after fe_enable_stage_timing(ctx, 1) (an event pair around every stage; CUDA-graph replay is
+ * bypassed while it is on). */
 int fe_enable_stage_timing(fe_ctx_t* ctx, int32_t enable);
 int fe_get_stage_times(fe_ctx_t* ctx, int32_t cap, const char** names, float* ms, int32_t* n);
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Source-level hot spots of one kernel from an ncu report (compiled with -lineinfo, captured with
---import-source on):  python tools/ncu_hot_lines.py <report.ncu-rep> [top]
+--import-source on):  python tools/ncu_hot_lines.py <report.ncu-rep> [top] [kernel-name regex]
 Prints, per CUDA source line, its share of executed warp instructions and of stall samples and the mean
 active lanes per instruction."""
 import csv
@@ -11,7 +11,8 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+    flt = ["-k", "regex:" + sys.argv[3], "-c", "1"] if len(sys.argv) > 3 else []
+    txt = subprocess.run(["ncu", "-i", rep] + flt + ["--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     cur, hdr, data = None, None, []
     for r in rows:
