@@ -72,7 +72,7 @@ struct Slot {
   // pinned host mirrors
   long long* h_scan_off = nullptr;
   int* h_chunk_off = nullptr;
-  int4 *h_chunkTab = nullptr, *d_chunkTab = nullptr;  // per chunk: scan, (chunk of scan << 12) | points, first point lo, hi
+  int4* d_chunkTab = nullptr;  // k_chunk_table, per chunk: scan, (chunk of scan << 12) | points, first point lo, hi
   float* h_rot = nullptr;
   DevCounters* h_ctr = nullptr;
   int* h_kpOff = nullptr;
@@ -270,7 +270,7 @@ void free_slot(Slot& s) {
                 s.d_kfCnt, s.d_kcBase, s.d_kcCnt, s.d_kpBase, s.d_kpCnt, s.d_kpOff, s.d_kpScan, s.d_kpNbr, s.d_kpNbrOff, s.d_kpRank, s.d_kpListM, s.d_kpListL, s.d_rowStart,
                 s.d_surfN, s.d_perScan, s.d_outOff, s.d_ovfRings, s.d_ovfRings2, s.d_ovfMerge, s.d_ovfMerge2, s.d_ovfSurf, s.d_slabs, s.d_gridHdr, s.d_tabOk, s.d_kfPool, s.d_kcPool, s.d_kpPool, s.d_kpOut, s.d_gather, s.d_desc, s.d_ctr, s.d_bnd, s.d_ringBase, s.d_ovfRuns, s.d_scanFlag, s.d_perScan2, s.d_outOff2, s.d_gather2, s.d_chunkTab};
   for (void* p : dv) if (p) cudaFree(p);
-  void* hv[] = {s.h_chunkTab, s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
+  void* hv[] = {s.h_scan_off, s.h_chunk_off, s.h_rot, s.h_ctr, s.h_kpOff, s.h_perScan, s.h_bnd, s.h_cloudOff, s.h_kcOff};
   for (void* p : hv) if (p) cudaFreeHost(p);
   for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
   for (GraphEntry& g : s.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -310,7 +310,7 @@ int ensure_slot(fe_ctx* ctx, Slot& s, bool ownPoints) {
   CK(dalloc(&s.d_rho, np));
   CK(dalloc(&s.d_scan_off, ns + 1)); CK(dalloc(&s.d_chunk_off, ns + 1));
   CK(dalloc(&s.d_surfCnt, (size_t)s.capChunks)); CK(dalloc(&s.d_cropCnt, (size_t)s.capChunks));
-  CK(dalloc(&s.d_chunkTab, (size_t)s.capChunks)); CK(halloc(&s.h_chunkTab, (size_t)s.capChunks));
+  CK(dalloc(&s.d_chunkTab, (size_t)s.capChunks));
   CK(dalloc(&s.d_rot, ns * 9));
   CK(dalloc(&s.d_kfBase, ns * 16)); CK(dalloc(&s.d_kfCnt, ns * 16));
   CK(dalloc(&s.d_kcBase, ns * 16)); CK(dalloc(&s.d_kcCnt, ns * 16));
@@ -361,8 +361,10 @@ std::string err_bits(int e) {
 int stage_scans_copy(fe_ctx* ctx, Slot& s, int nscans, bool deferRot) {
   CK(cudaMemcpyAsync(s.d_scan_off, s.h_scan_off, (nscans + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_chunk_off, s.h_chunk_off, (nscans + 1) * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-  const int nch = s.h_chunk_off[nscans];
-  if (nch > 0) CK(cudaMemcpyAsync(s.d_chunkTab, s.h_chunkTab, (size_t)nch * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
+  if (s.h_chunk_off[nscans] > 0) {  // K1's chunk -> scan table, built where the offsets just landed
+    k_chunk_table<<<(nscans + 7) / 8, 256, 0, s.stream>>>(s.d_scan_off, s.d_chunk_off, nscans, s.d_chunkTab);
+    ctx->launches++;
+  }
   if (!deferRot) CK(cudaMemcpyAsync(s.d_rot, s.h_rot, (size_t)nscans * 9 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
   return FE_OK;
 }
@@ -384,11 +386,6 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
     s.h_chunk_off[i] = nch;
     const int64_t nc = (n + CH - 1) / CH;
     if (nc > (int64_t)s.capChunks - nch) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds the chunk capacity");
-    for (int64_t c = 0; c < nc; c++) {  // K1's chunk table (k_level_crop_ring)
-      const int64_t b = offs[i] - o0 + c * CH;
-      s.h_chunkTab[nch + c] = make_int4(i, (int)(((unsigned)c << 12) | (unsigned)std::min<int64_t>(CH, n - c * CH)),
-                                        (int)(unsigned)(b & 0xFFFFFFFFll), (int)(b >> 32));
-    }
     nch += (int)nc;
     if (deferRot) continue;  // enqueue_pipeline computes the matrices range by range (lateRp)
     if (rp) leveling_matrix(rp[2 * i], rp[2 * i + 1], s.h_rot + 9 * i);

@@ -159,6 +159,20 @@ struct RawLayout {  // records of fe_point_layout_t; raw == nullptr: the input i
   int stride, xo, yo, zo;
 };
 
+// K1's chunk table: per chunk {scan, (chunk of the scan << 12) | points, first point lo, hi}.  One warp per scan.
+__global__ void __launch_bounds__(256) k_chunk_table(const long long* __restrict__ scan_off, const int* __restrict__ chunk_off,
+                                                      int n_scans, int4* __restrict__ tab) {
+  const int s = (int)((blockIdx.x * 256u + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= n_scans) return;
+  const long long b0 = scan_off[s], n = scan_off[s + 1] - b0;
+  const int c0 = chunk_off[s], nc = chunk_off[s + 1] - c0;
+  for (int c = lane; c < nc; c += 32) {
+    const long long b = b0 + (long long)c * CH;
+    tab[c0 + c] = make_int4(s, (int)(((unsigned)c << 12) | (unsigned)min((long long)CH, n - (long long)c * CH)),
+                            (int)(unsigned)(b & 0xFFFFFFFFll), (int)(b >> 32));
+  }
+}
+
 // ============================================================================================
 // K1 — fused elevation / level / crop / ring-bucket, order-preserving compaction per chunk.
 // Block = one chunk of CH consecutive points of one scan; 256 threads; warp w owns points
