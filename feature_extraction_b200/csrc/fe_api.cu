@@ -451,7 +451,8 @@ const size_t kClusterSmemM = cluster_smem_bytes(ECAP_M, NTM);
 
 int set_kernel_attrs(fe_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP, NTF, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-  CK(cudaFuncSetAttribute(k_ring_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingRunsSmT<RW>)));
+  CK(cudaFuncSetAttribute(k_ring_runs<NW_RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingRunsSmT<RW>)));
+  CK(cudaFuncSetAttribute(k_ring_runs<NW_RR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingRunsSmT<RW, NW_RR_SMALL>)));
   CK(cudaFuncSetAttribute(k_ring_runs_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NW_RR * sizeof(RunBufT<RW2>))));
   CK(cudaFuncSetAttribute(k_cluster_rings<ECAP_L, NTL, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemL2));
   CK(cudaFuncSetAttribute(k_merge_keypoints<ECAP_M, NTM, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemM));
@@ -472,14 +473,17 @@ int set_kernel_attrs(fe_ctx* ctx) {
 void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp, bool records) {
   const int descStride = records ? FE_RECORD_FLOATS : FE_DESC_LEN, descOff = records ? 5 : 0;
 #define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, \
-                     s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, FE_DESC_LIST, s.d_desc, descStride, descOff, s.d_ctr
+                     s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, FE_DESC_LIST, s.d_desc, descStride, descOff, s.d_ctr, warpCap
   // the blocks stride over the keypoints with equal shares: grids of exactly one resident wave
   static const int perSm = []() {  // initialised once, also when fe_multi's threads get here together
     int v = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist<256, DCAP, DW_CAP, false, true>, 256, desc_smem_bytes(DCAP, 256)) != cudaSuccess) v = 4;
     return v;
   }();
-  {  // keypoints with at most DW_CAP listed neighbours (and the empty ones): a warp each
+  // A handful of scans (the reference's one scan per callback) has too few keypoints to fill the GPU with warps:
+  // there every keypoint gets a block (several times shorter per keypoint) and the warp kernel is not launched.
+  const int warpCap = nscans <= GRAPH_MAX_SCANS ? -1 : DW_CAP;
+  if (warpCap >= 0) {  // keypoints with at most DW_CAP listed neighbours (and the empty ones): a warp each
     static const int perSmW = []() {
       int v = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist_warp, DW_WARPS * 32, desc_warp_smem_bytes()) != cudaSuccess) v = 2;
@@ -588,10 +592,13 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
     k_cluster_rings<ECAP, NTF, 4, false><<<nscans, NTF, kClusterSmem, s.stream>>>(FE_K2_ARGS, nullptr, nullptr, s.d_ovfRings, ovfR, nullptr);
   else
   {
-    k_ring_runs<<<nscans, NT_RR, sizeof(RingRunsSmT<RW>), s.stream>>>(s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr,
-                                                                      s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc,
-                                                                      s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag,
-                                                                      s.d_ovfRings, ovfR);
+#define FE_RR_ARGS s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, \
+                   s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag, s.d_ovfRings, ovfR
+    if (nscans <= GRAPH_MAX_SCANS)  // a handful of scans: a warp for each of a scan's 16 rings at once (latency, not throughput)
+      k_ring_runs<NW_RR_SMALL><<<nscans, NW_RR_SMALL * 32, sizeof(RingRunsSmT<RW, NW_RR_SMALL>), s.stream>>>(FE_RR_ARGS);
+    else
+      k_ring_runs<NW_RR><<<nscans, NT_RR, sizeof(RingRunsSmT<RW>), s.stream>>>(FE_RR_ARGS);
+#undef FE_RR_ARGS
     k_ring_runs_wide<<<std::min(nscans * 4, ctx->numSms * 7), NT_RR, NW_RR * sizeof(RunBufT<RW2>), s.stream>>>(
         s.d_scan_off, P, s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC, s.d_ctr,
         s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag, s.d_ovfRings, ovfR);

@@ -1933,7 +1933,7 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
     const unsigned* __restrict__ nbrPool, const int* __restrict__ kpNbrOff, const int* __restrict__ kpRank,
     const int* __restrict__ glist, const int* __restrict__ nlist, float* __restrict__ desc, int descStride, int descOff,
-    DevCounters* __restrict__ ctr) {
+    DevCounters* __restrict__ ctr, int warpCap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keyA = (unsigned long long*)smem_raw;
   unsigned long long* keyB = keyA + CAP;
@@ -1968,7 +1968,9 @@ __global__ void __launch_bounds__(NT) k_desc_hist(
     float* out = desc + (long long)g * descStride + descOff;
     const int nb = kpNbr[g];
     if (!LAST && nb > CAP) continue;           // a larger instantiation's keypoint
-    if (NB_MIN > 0 && nb <= NB_MIN && (nb == 0 || kpNbrOff[g] >= 0)) continue;  // the warp kernel's keypoint
+    // warpCap = min(NB_MIN, what the host lets the warp kernel take: -1 for a handful of scans, where a block per
+    // keypoint finishes sooner than a warp per keypoint)
+    if (NB_MIN > 0 && nb <= warpCap && (nb == 0 || kpNbrOff[g] >= 0)) continue;  // the warp kernel's keypoint
     if (nb == 0) {  // no neighbour (or non-finite keypoint): descriptor is NaN (3dsc.hpp)
       for (int i = tid; i < FE_DESC_LEN; i += NT) out[i] = __int_as_float(0x7fc00000);
       continue;

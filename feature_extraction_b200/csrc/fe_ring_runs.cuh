@@ -37,15 +37,17 @@ struct RunBufT {                 // one per warp, shared memory
   static constexpr int cap = RWT;
 };
 
-template <int RWT>
+constexpr int NW_RR_SMALL = 16;  // warps per scan block when a call holds only a handful of scans: a warp per ring at once
+
+template <int RWT, int NW = NW_RR>
 struct RingRunsSmT {
   int pre[MAXCHUNK + 1];
   int sc[40];
-  int cnt[NW_RR][17];            // phase A: entries per (warp, ring); [16] = entries in no ring
+  int cnt[NW][17];               // phase A: entries per (warp, ring); [16] = entries in no ring
   int ringBase[18];
   int nextRing;
   int defer;
-  RunBufT<RWT> rb[NW_RR];
+  RunBufT<RWT> rb[NW];
 };
 
 __device__ __forceinline__ int f2ord(float f) {  // monotone float -> int
@@ -323,8 +325,8 @@ __device__ bool rr_cluster_ring(RB& B, const float4* P, const int n, const DevPa
 // Phase B for one scan whose ring segments [ringBase[r], ringBase[r+1]) are in place at RP: the warps take rings
 // off the block's counter.  A ring with more runs than a warp's buffer holds is listed for the wide kernel (its
 // outputs are untouched); the other rings of the scan are finished here.
-template <int RWT>
-__device__ void rr_scan_rings(RingRunsSmT<RWT>& S, const int s, const float4* RP, const int nRings, const DevParams& P,
+template <int RWT, int NW>
+__device__ void rr_scan_rings(RingRunsSmT<RWT, NW>& S, const int s, const float4* RP, const int nRings, const DevParams& P,
                               float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
                               float4* __restrict__ kcPool, int kcCap, int* __restrict__ kcBase, int* __restrict__ kcCnt,
                               DevCounters* __restrict__ ctr, int* __restrict__ ovfRuns, int* __restrict__ ovfRunsCount) {
@@ -346,7 +348,8 @@ __device__ void rr_scan_rings(RingRunsSmT<RWT>& S, const int s, const float4* RP
 // First kernel: one block per scan, every scan.  A ring of more than RW runs is handed to the second kernel (the
 // ring segments and their offsets stay in global memory, so nothing is bucketed twice); a scan with more ring
 // entries than its scratch slot goes straight to the grid-based kernels.
-__global__ void __launch_bounds__(NT_RR, 12) k_ring_runs(
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == NW_RR ? 12 : 1) k_ring_runs(
     const float4* __restrict__ crop, const unsigned* __restrict__ cropMeta, const int* __restrict__ cropCnt,
     const long long* __restrict__ scan_off, const int* __restrict__ chunk_off, DevParams P, int single_ring,
     float4* ringPts, int* __restrict__ ringBaseOut, float4* __restrict__ kfPool, int kfCap, int* __restrict__ kfBase, int* __restrict__ kfCnt,
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(NT_RR, 12) k_ring_runs(
     DevCounters* __restrict__ ctr, int* __restrict__ ovfRuns, int* __restrict__ ovfRunsCount, int* __restrict__ scanFlag,
     int* __restrict__ ovfList, int* __restrict__ ovfCount) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RingRunsSmT<RW>& S = *reinterpret_cast<RingRunsSmT<RW>*>(smem_raw);
+  RingRunsSmT<RW, NW>& S = *reinterpret_cast<RingRunsSmT<RW, NW>*>(smem_raw);
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const long long base = scan_off[s];
   const int nScan = (int)(scan_off[s + 1] - base);
@@ -362,14 +365,14 @@ __global__ void __launch_bounds__(NT_RR, 12) k_ring_runs(
   if (tid < 16) { kfBase[s * 16 + tid] = 0; kfCnt[s * 16 + tid] = 0; if (kcBase) { kcBase[s * 16 + tid] = 0; kcCnt[s * 16 + tid] = 0; } }
   if (tid == 0) scanFlag[s] = 0;  // the wide kernel sets it when it sends the scan on to the grid-based kernels
   if (nch > MAXCHUNK) { if (tid == 0) atomicOr(&ctr->err, ERR_CHUNKS); return; }
-  if (tid < NW_RR * 17) (&S.cnt[0][0])[tid] = 0;
+  if (tid < NW * 17) (&S.cnt[0][0])[tid] = 0;
   if (tid == 0) { S.nextRing = 0; S.defer = 0; }
-  const int Nc = chunk_prefix<NT_RR>(cropCnt + chunk_off[s], nch, S.pre, S.sc);  // ends with a barrier
+  const int Nc = chunk_prefix<NW * 32>(cropCnt + chunk_off[s], nch, S.pre, S.sc);  // ends with a barrier
   if (Nc == 0) return;
   const int nRings = single_ring ? 1 : 16;
   // ---- phase A: stable bucketing of the crop survivors by ring ----
   // every warp owns a contiguous range of the survivors; (1) per-warp counts, (2) offsets, (3) scatter
-  const int lo = (int)((long long)Nc * w / NW_RR), hi = (int)((long long)Nc * (w + 1) / NW_RR);
+  const int lo = (int)((long long)Nc * w / NW), hi = (int)((long long)Nc * (w + 1) / NW);
   int* mycnt = S.cnt[w];
   for (int i0 = lo; i0 < hi; i0 += 32) {
     const int i = i0 + lane;
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(NT_RR, 12) k_ring_runs(
   if (tid < 16) {
     // S.cnt[w][h] becomes the first slot of warp w's entries of ring h inside the ring's segment
     int run = 0;
-    for (int ww = 0; ww < NW_RR; ww++) { const int c = S.cnt[ww][tid]; S.cnt[ww][tid] = run; run += c; }
+    for (int ww = 0; ww < NW; ww++) { const int c = S.cnt[ww][tid]; S.cnt[ww][tid] = run; run += c; }
     S.ringBase[tid + 1] = run;  // totals for now
   }
   __syncthreads();
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(NT_RR, 12) k_ring_runs(
   __syncthreads();  // the block's global writes are visible to all its threads from here on
   // ---- phase B: a warp per ring, rings handed out dynamically ----
   if (tid < 17) ringBaseOut[s * 17 + tid] = S.ringBase[tid];  // for the wide kernel, should a ring of this scan need it
-  rr_scan_rings<RW>(S, s, RP, nRings, P, kfPool, kfCap, kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfRuns, ovfRunsCount);
+  rr_scan_rings<RW, NW>(S, s, RP, nRings, P, kfPool, kfCap, kfBase, kfCnt, kcPool, kcCap, kcBase, kcCnt, ctr, ovfRuns, ovfRunsCount);
 }
 
 // Second kernel: the rings the first one listed (hundreds of poles in one ring), a warp per ring with RW2 runs;
