@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Source-level hot spots of one kernel from an ncu report (compiled with -lineinfo, captured with
---import-source on):  python tools/ncu_hot_lines.py <report.ncu-rep> [top] [kernel-name regex]
+--import-source on):  python tools/ncu_hot_lines.py <report.ncu-rep> [top] [kernel-name regex | launch index in the report]
 Prints, per CUDA source line, its share of executed warp instructions and of stall samples and the mean
 active lanes per instruction."""
 import csv
@@ -11,7 +11,9 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    flt = ["-k", "regex:" + sys.argv[3], "-c", "1"] if len(sys.argv) > 3 else []
+    flt = []
+    if len(sys.argv) > 3:
+        flt = ["--launch-skip", sys.argv[3], "-c", "1"] if sys.argv[3].isdigit() else ["-k", "regex:" + sys.argv[3], "-c", "1"]
     txt = subprocess.run(["ncu", "-i", rep] + flt + ["--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     cur, hdr, data = None, None, []
@@ -21,7 +23,8 @@ def main():
         elif len(r) > 8 and r[0] == "Line No":
             hdr = r
         elif hdr and len(r) == len(hdr) and r[2] == "-":  # a source line (SASS rows carry an address)
-            iI, iS, iT = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+            iS = hdr.index("# Samples") if "# Samples" in hdr else hdr.index("Warp Stall Sampling (All Samples)")
+            iI, iT = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
             try:
                 data.append((int(r[iI]), int(r[iS]), int(r[iT]), cur, r[0], r[1]))
             except ValueError:
