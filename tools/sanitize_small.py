@@ -1,7 +1,8 @@
 """A small pass of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool memcheck python tools/sanitize_small.py
 Covers: fused batch (configs 1-4, few scans), unordered input (grid fallback of K2), boundary report, cloud outputs,
-record output, stage entry points, single-scan graph replay."""
+record output, stage entry points, single-scan graph replay, and one call of more than 16 scans (the throughput
+instantiations of K2 and K4d; calls of at most 16 scans run the latency ones)."""
 import os
 import sys
 
@@ -42,3 +43,11 @@ for cfg, n in ((1, 2), (2, 3), (3, 1), (4, 1)):
     nd.extractClusters(rc[:2000], 0.65, 1, 1000)
     print("config", cfg, "ok:", len(kp), "keypoints")
     nd.close()
+
+# more than 16 scans in one call: the batch instantiations (k_ring_runs<4>, k_desc_hist_warp)
+P = node_default()
+pts, offs, rp = synth.generate(2, 20, scan_index_base=177)
+nd = FeatureExtractionNode(P, max_points=1 << 19, max_scans=32, max_keypoints=4096)
+ko, kp, d = nd.processBatch(pts, offs, rp)
+print("batch of 20 ok:", len(kp), "keypoints")
+nd.close()
