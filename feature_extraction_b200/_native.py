@@ -139,6 +139,7 @@ def lib():
         L.fe_multi_get_cloud_outputs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_void_p),
                                                  C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_void_p)]
         L.fe_debug_enable_graphs.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
+        L.fe_debug_lean_reruns.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.fe_debug_density_work.argtypes = [C.c_void_p, C.c_void_p]
         L.fe_debug_h2d_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float)]
         L.fe_debug_force_grid_clustering.argtypes = [C.c_void_p, C.c_int32]

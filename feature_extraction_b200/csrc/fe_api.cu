@@ -25,7 +25,8 @@ namespace {
 constexpr int GRAPH_MAX_SCANS = 16;
 struct GraphKey {
   int nscans, nch, by, k1flags, stride, xo, yo, zo;
-  int desc, wantKc, bnd, epoch;
+  int desc, wantKc, bnd, epoch, lean;
+  const void* pts;  // device-resident input (fe_process_batch_device): the pointer is part of the captured launches
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry {
@@ -36,6 +37,11 @@ struct GraphEntry {
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  // lean chain (see process_batch_host): what finalize_subbatch needs to run the sub-batch again with every fallback kernel
+  bool lean = false;
+  const float4* rrPts = nullptr;
+  int rrNch = 0, rrK1flags = 0, rrStride = 0, rrXo = 0, rrYo = 0, rrZo = 0;
+  bool rrDesc = false, rrWantKc = false, rrRaw = false;
   std::vector<GraphEntry> graphs;
   int64_t capPts = 0;
   int capScans = 0, capChunks = 0;
@@ -107,6 +113,8 @@ struct fe_ctx {
   float2* d_axes = nullptr;
   int axesCap = 0;
   bool cloudOutputs = false;
+  int leanHold = 0;           // sub-batches for which the lean chain stays off after one had to be run again
+  int64_t leanReruns = 0;
   bool stageTiming = false;   // serialise the stages and time each with CUDA events (fe_enable_stage_timing)
   bool gridClustering = false;  // fe_debug_force_grid_clustering: K2 through the grid-based kernels only
   bool recordOutput = false;  // descriptors leave as FE_RECORD_FLOATS-float PointDescriptor records
@@ -470,7 +478,7 @@ int set_kernel_attrs(fe_ctx* ctx) {
 }
 
 // K4d: three instantiations split the keypoints by neighbour count (smaller footprint = more blocks / SM)
-void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp, bool records) {
+void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int gridKp, bool records, bool lean = false) {
   const int descStride = records ? FE_RECORD_FLOATS : FE_DESC_LEN, descOff = records ? 5 : 0;
 #define FE_DESC_ARGS s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, surf_index(ctx, s), s.d_scan_off, P, \
                      s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap, s.d_keyA, s.d_kpNbrOff, s.d_kpRank, FE_DESC_LIST, s.d_desc, descStride, descOff, s.d_ctr, warpCap
@@ -498,14 +506,17 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
 #define FE_DESC_LIST nullptr, nullptr
   k_desc_hist<256, DCAP, DW_CAP, false, true><<<std::min(gridKp, ctx->numSms * std::max(perSm, 1)), 256, desc_smem_bytes(DCAP, 256), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
+  ctx->launches++;
+  if (!lean) {  // lean: keypoints listed for the two larger instantiations make the caller run the sub-batch again
 #define FE_DESC_LIST s.d_kpListM, &s.d_ctr->n_list_m
   k_desc_hist<512, DCAP_M, DCAP, false, false><<<std::min(gridKp, ctx->numSms * 2), 512, desc_smem_bytes(DCAP_M, 512), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
 #define FE_DESC_LIST s.d_kpListL, &s.d_ctr->n_list_l
   k_desc_hist<512, DCAP_L, DCAP_M, true, false><<<std::min(gridKp, ctx->numSms), 512, desc_smem_bytes(DCAP_L, 512), s.stream>>>(FE_DESC_ARGS);
 #undef FE_DESC_LIST
+  ctx->launches += 2;
+  }
 #undef FE_DESC_ARGS
-  ctx->launches += 3;
   if (records) {
     k_record_frame<<<ctx->numSms * 2, 256, 0, s.stream>>>(s.d_kpOut, s.d_kpOff, nscans, s.d_desc, descStride, FE_DESC_LEN);
     ctx->launches++;
@@ -569,7 +580,7 @@ void launch_density(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int64_
 // whatever scans it deferred (an immediate exit when there are none).
 void mark(fe_ctx* ctx, Slot& s, const char* name);
 
-void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool wantKc, bool merge, bool marks = false) {
+void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool wantKc, bool merge, bool marks = false, bool lean = false) {
   // Every stage is a chain of instantiations: the fast one takes all scans and defers those that do
   // not fit its shared memory to a list; the large shared-memory one takes that list; what does not
   // fit there either goes to the instantiation whose per-entry arrays live in global memory.
@@ -588,10 +599,10 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
                    s.capKc, kcB, kcC, s.d_ctr
   // K2: the run-based kernel takes every scan; what it cannot handle (a ring with more than RW runs — unordered
   // input — or more ring entries than the scan's scratch slot) goes down the chain of grid-based instantiations.
-  if (ctx->gridClustering)
+  if (ctx->gridClustering) {
     k_cluster_rings<ECAP, NTF, 4, false><<<nscans, NTF, kClusterSmem, s.stream>>>(FE_K2_ARGS, nullptr, nullptr, s.d_ovfRings, ovfR, nullptr);
-  else
-  {
+    ctx->launches++;
+  } else {
 #define FE_RR_ARGS s.d_crop, s.d_cropMeta, s.d_cropCnt, s.d_scan_off, s.d_chunk_off, P, sr, s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, \
                    s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC, s.d_ctr, s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag, s.d_ovfRings, ovfR
     if (nscans <= GRAPH_MAX_SCANS)  // a handful of scans: a warp for each of a scan's 16 rings at once (latency, not throughput)
@@ -599,23 +610,33 @@ void launch_clustering(fe_ctx* ctx, Slot& s, int nscans, bool singleRing, bool w
     else
       k_ring_runs<NW_RR><<<nscans, NT_RR, sizeof(RingRunsSmT<RW>), s.stream>>>(FE_RR_ARGS);
 #undef FE_RR_ARGS
-    k_ring_runs_wide<<<std::min(nscans * 4, ctx->numSms * 7), NT_RR, NW_RR * sizeof(RunBufT<RW2>), s.stream>>>(
-        s.d_scan_off, P, s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC, s.d_ctr,
-        s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag, s.d_ovfRings, ovfR);
     ctx->launches++;
+    if (!lean) {
+      k_ring_runs_wide<<<std::min(nscans * 4, ctx->numSms * 7), NT_RR, NW_RR * sizeof(RunBufT<RW2>), s.stream>>>(
+          s.d_scan_off, P, s.d_ringPts, s.d_ringBase, s.d_kfPool, s.capKf, s.d_kfBase, s.d_kfCnt, kc, s.capKc, kcB, kcC, s.d_ctr,
+          s.d_ovfRuns, &s.d_ctr->ovf_runs, s.d_scanFlag, s.d_ovfRings, ovfR);
+      ctx->launches++;
+    }
   }
-  k_cluster_rings<ECAP_L, NTL, 1, false><<<gridL, NTL, kClusterSmemL2, s.stream>>>(FE_K2_ARGS, s.d_ovfRings, ovfR, s.d_ovfRings2, ovfR2, nullptr);
-  k_cluster_rings<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K2_ARGS, s.d_ovfRings2, ovfR2, nullptr, nullptr, s.d_slabs);
+  // lean: the fallback instantiations are left out; whatever the first kernel deferred shows in the counters and the
+  // caller runs the sub-batch again with the whole chain
+  if (!lean) {
+    k_cluster_rings<ECAP_L, NTL, 1, false><<<gridL, NTL, kClusterSmemL2, s.stream>>>(FE_K2_ARGS, s.d_ovfRings, ovfR, s.d_ovfRings2, ovfR2, nullptr);
+    k_cluster_rings<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K2_ARGS, s.d_ovfRings2, ovfR2, nullptr, nullptr, s.d_slabs);
+    ctx->launches += 2;
+  }
 #undef FE_K2_ARGS
-  ctx->launches += 3;
   if (marks) mark(ctx, s, "K2 ring clusters");
   if (merge) {
 #define FE_K3_ARGS s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, s.d_kpPool, (int)s.capKp, s.d_kpBase, s.d_kpCnt, s.d_ctr
     k_merge_keypoints<ECAP_M, NTM, 8, false><<<nscans, NTM, kClusterSmemM, s.stream>>>(FE_K3_ARGS, nullptr, nullptr, s.d_ovfMerge, ovfM, nullptr);
-    k_merge_keypoints<ECAP_L, NT2, 1, false><<<gridL, NT2, kClusterSmemL, s.stream>>>(FE_K3_ARGS, s.d_ovfMerge, ovfM, s.d_ovfMerge2, ovfM2, nullptr);
-    k_merge_keypoints<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K3_ARGS, s.d_ovfMerge2, ovfM2, nullptr, nullptr, s.d_slabs);
+    ctx->launches++;
+    if (!lean) {
+      k_merge_keypoints<ECAP_L, NT2, 1, false><<<gridL, NT2, kClusterSmemL, s.stream>>>(FE_K3_ARGS, s.d_ovfMerge, ovfM, s.d_ovfMerge2, ovfM2, nullptr);
+      k_merge_keypoints<ECAP_G, NT2, 1, true><<<gridG, NT2, smemG, s.stream>>>(FE_K3_ARGS, s.d_ovfMerge2, ovfM2, nullptr, nullptr, s.d_slabs);
+      ctx->launches += 2;
+    }
 #undef FE_K3_ARGS
-    ctx->launches += 3;
   }
 }
 
@@ -645,7 +666,7 @@ int ensure_bnd(fe_ctx* ctx, Slot& s) {
 // `fromStage`: 0 = K1 first; 1 = crop/cropMeta/cropCnt already filled by the caller.
 int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int64_t npts, int nch,
                      int k1flags, bool doDesc, bool singleRing, bool wantKc, RawLayout lay = RawLayout{nullptr, 0, 0, 0, 0},
-                     const double* lateRp = nullptr, bool recordDone = true) {
+                     const double* lateRp = nullptr, bool recordDone = true, bool lean = false) {
   DevParams& P = ctx->dp;
   s.nev = 0;
   mark(ctx, s, "begin");
@@ -694,7 +715,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     int st = ensure_rowstart(ctx, s, nscans);
     if (st) return st;
   }
-  launch_clustering(ctx, s, nscans, singleRing, wantKc, true, true);
+  launch_clustering(ctx, s, nscans, singleRing, wantKc, true, true, lean);
   mark(ctx, s, "K3 merge keypoints");
   if (bnd) {
     k_boundary_merge<<<nscans, 128, 0, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, boundary_spec(ctx), s.d_bnd);
@@ -723,7 +744,7 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     }
     launch_density(ctx, s, nscans, P, npts);
     mark(ctx, s, "K4c density");
-    launch_desc_hist(ctx, s, nscans, P, gridKp, ctx->recordOutput);
+    launch_desc_hist(ctx, s, nscans, P, gridKp, ctx->recordOutput, lean);
     mark(ctx, s, "K4d shape context");
   }
   if (wantKc && ctx->cloudOutputs && nscans > 0) {
@@ -794,10 +815,90 @@ int grow_pinned_points(fe_ctx* ctx, fe_point_t** buf, int64_t* cap, int64_t used
 }
 
 // wait for the sub-batch in `s`, check its error word, append its keypoints to the results
+// The sub-batch ran the lean chain (first instantiation of every stage only, see enqueue_small).  Anything one of
+// them deferred to a fallback kernel is in the counters: run the sub-batch again, eagerly, with the whole chain (its
+// points and staged offsets are still where they were), and keep the lean chain off for a while — inputs that defer
+// once (unordered clouds, very large descriptor radii) usually keep doing so.  Call after the slot's evDone.
+int lean_rerun_if_deferred(fe_ctx* ctx, Slot& s) {
+  if (!s.lean) return FE_OK;
+  s.lean = false;
+  const DevCounters& c = *s.h_ctr;
+  if (c.err || !(c.ovf_runs | c.ovf_rings | c.ovf_rings2 | c.ovf_merge | c.ovf_merge2 | c.n_list_m | c.n_list_l)) return FE_OK;
+  ctx->leanHold = 256;
+  ctx->leanReruns++;
+  RawLayout lay = {s.rrRaw ? (const unsigned char*)s.rrPts : nullptr, s.rrStride, s.rrXo, s.rrYo, s.rrZo};
+  int st = enqueue_pipeline(ctx, s, s.rrPts, s.nscans, s.npts, s.rrNch, s.rrK1flags, s.rrDesc, false, s.rrWantKc, lay);
+  if (st) return st;
+  CK(cudaEventSynchronize(s.evDone));
+  return FE_OK;
+}
+
+// A sub-batch of at most GRAPH_MAX_SCANS scans whose offsets stage_scans(copy = false) left in the pinned mirrors:
+// the chain is captured into a CUDA graph per shape (second sighting) and replayed from then on.  Lean chain: a
+// handful of scans almost never needs a fallback instantiation, and seven kernels that only find that out cost more
+// than a tenth of a single scan's latency; they are left out and lean_rerun_if_deferred repairs the rare miss.
+// Records the slot's evDone.
+int enqueue_small(fe_ctx* ctx, Slot& s, const float4* d_pts, bool ptsInKey, int ns, int64_t npts, int nch, int k1flags, bool desc,
+                  bool wantKc, RawLayout lay) {
+  int st;
+  // every allocation the pipeline may need happens before a capture starts
+  if (desc) { st = ensure_rowstart(ctx, s, ns); if (st) return st; }
+  if (ctx->bndEps > 0.0) { st = ensure_bnd(ctx, s); if (st) return st; }
+  GraphKey key;
+  memset(&key, 0, sizeof key);
+  key.nscans = ns; key.nch = nch; key.by = density_blocks_per_scan(ns, npts); key.k1flags = k1flags | ((s.maxScanPts > 65535) ? (1 << 16) : 0);
+  key.stride = lay.raw ? lay.stride : 0; key.xo = lay.xo; key.yo = lay.yo; key.zo = lay.zo;
+  key.desc = desc; key.wantKc = wantKc; key.bnd = ctx->bndEps > 0.0; key.epoch = ctx->epoch;
+  key.pts = ptsInKey ? (const void*)d_pts : nullptr;
+  const bool lean = ctx->leanHold == 0;
+  if (ctx->leanHold > 0) ctx->leanHold--;
+  key.lean = lean;
+  s.lean = lean; s.rrPts = d_pts; s.rrNch = nch; s.rrK1flags = k1flags; s.rrDesc = desc; s.rrWantKc = wantKc;
+  s.rrRaw = lay.raw != nullptr; s.rrStride = lay.stride; s.rrXo = lay.xo; s.rrYo = lay.yo; s.rrZo = lay.zo;
+  GraphEntry* ge = nullptr;
+  for (GraphEntry& g : s.graphs) if (g.key == key) { ge = &g; break; }
+  if (ge && ge->exec) {  // replay
+    CK(cudaGraphLaunch(ge->exec, s.stream));
+    ctx->launches += ge->launches;
+    ctx->graphReplays++;
+  } else if (!ge) {      // first sighting of the shape: eager, so that every lazily initialised piece exists
+    st = stage_scans_copy(ctx, s, ns, false);
+    if (st) return st;
+    st = enqueue_pipeline(ctx, s, d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay, nullptr, false, lean);
+    if (st) return st;
+    if (s.graphs.size() >= 16) {  // drop the oldest shape
+      if (s.graphs[0].exec) cudaGraphExecDestroy(s.graphs[0].exec);
+      s.graphs.erase(s.graphs.begin());
+    }
+    GraphEntry e; e.key = key;
+    s.graphs.push_back(e);
+  } else {               // second sighting: capture, instantiate, launch
+    const int64_t l0 = ctx->launches;
+    CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+    st = stage_scans_copy(ctx, s, ns, false);
+    if (st == FE_OK) st = enqueue_pipeline(ctx, s, d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay, nullptr, false, lean);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s.stream, &graph);
+    if (st) { if (graph) cudaGraphDestroy(graph); return st; }
+    if (ce != cudaSuccess) return fail(ctx, FE_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess) return fail(ctx, FE_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ci));
+    ge->exec = exec;
+    ge->launches = ctx->launches - l0;
+    CK(cudaGraphLaunch(exec, s.stream));
+    ctx->graphReplays++;
+  }
+  CK(cudaEventRecord(s.evDone, s.stream));
+  return FE_OK;
+}
+
 int finalize_subbatch(fe_ctx* ctx, Slot& s, int64_t& kpRun, bool desc) {
   if (!s.busy) return FE_OK;
   CK(cudaEventSynchronize(s.evDone));
   s.busy = false;
+  { int st = lean_rerun_if_deferred(ctx, s); if (st) return st; }
   if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
   const int K = s.h_kpOff[s.nscans];
   int st = grow_results(ctx, kpRun + K, desc);
@@ -1122,53 +1223,12 @@ static int process_batch_host(fe_ctx_t* ctx, const unsigned char* points, int st
     RawLayout lay = {isFloat4 ? nullptr : (const unsigned char*)s.d_pts, stride, xo, yo, zo};
     const int k1flags = F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0);
     if (!graphable) {
+      s.lean = false;
       st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay);
       if (st) return st;
     } else {
-      // every allocation the pipeline may need happens before a capture starts
-      if (desc) { st = ensure_rowstart(ctx, s, ns); if (st) return st; }
-      if (ctx->bndEps > 0.0) { st = ensure_bnd(ctx, s); if (st) return st; }
-      GraphKey key;
-      memset(&key, 0, sizeof key);
-      key.nscans = ns; key.nch = nch; key.by = density_blocks_per_scan(ns, npts); key.k1flags = k1flags | ((s.maxScanPts > 65535) ? (1 << 16) : 0);
-      key.stride = isFloat4 ? 0 : stride; key.xo = xo; key.yo = yo; key.zo = zo;
-      key.desc = desc; key.wantKc = wantKc; key.bnd = ctx->bndEps > 0.0; key.epoch = ctx->epoch;
-      GraphEntry* ge = nullptr;
-      for (GraphEntry& g : s.graphs) if (g.key == key) { ge = &g; break; }
-      if (ge && ge->exec) {  // replay
-        CK(cudaGraphLaunch(ge->exec, s.stream));
-        ctx->launches += ge->launches;
-        ctx->graphReplays++;
-      } else if (!ge) {      // first sighting of the shape: eager, so that every lazily initialised piece exists
-        st = stage_scans_copy(ctx, s, ns, false);
-        if (st) return st;
-        st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay, nullptr, false);
-        if (st) return st;
-        if (s.graphs.size() >= 16) {  // drop the oldest shape
-          if (s.graphs[0].exec) cudaGraphExecDestroy(s.graphs[0].exec);
-          s.graphs.erase(s.graphs.begin());
-        }
-        GraphEntry e; e.key = key;
-        s.graphs.push_back(e);
-      } else {               // second sighting: capture, instantiate, launch
-        const int64_t l0 = ctx->launches;
-        CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
-        st = stage_scans_copy(ctx, s, ns, false);
-        if (st == FE_OK) st = enqueue_pipeline(ctx, s, s.d_pts, ns, npts, nch, k1flags, desc, false, wantKc, lay, nullptr, false);
-        cudaGraph_t graph = nullptr;
-        const cudaError_t ce = cudaStreamEndCapture(s.stream, &graph);
-        if (st) { if (graph) cudaGraphDestroy(graph); return st; }
-        if (ce != cudaSuccess) return fail(ctx, FE_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
-        cudaGraphExec_t exec = nullptr;
-        const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ci != cudaSuccess) return fail(ctx, FE_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ci));
-        ge->exec = exec;
-        ge->launches = ctx->launches - l0;
-        CK(cudaGraphLaunch(exec, s.stream));
-        ctx->graphReplays++;
-      }
-      CK(cudaEventRecord(s.evDone, s.stream));
+      st = enqueue_small(ctx, s, s.d_pts, false, ns, npts, nch, k1flags, desc, wantKc, lay);
+      if (st) return st;
     }
     s.busy = true; s.nscans = ns; s.npts = npts; s.firstScan = first;
     nsub++;
@@ -1257,13 +1317,23 @@ int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points, const int
   int64_t npts = 0; int nch = 0;
   if (n_scans > 0) {
     const bool late = n_scans >= 2048;
-    st = stage_scans(ctx, s, scan_offsets, roll_pitch, n_scans, &npts, &nch, late);
+    const bool small = ctx->useGraphs && !ctx->stageTiming && n_scans <= GRAPH_MAX_SCANS;
+    const int k1flags = F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0);
+    const float4* d_pts = (const float4*)d_points + scan_offsets[0];
+    st = stage_scans(ctx, s, scan_offsets, roll_pitch, n_scans, &npts, &nch, late, !small);
     if (st) return st;
-    st = enqueue_pipeline(ctx, s, (const float4*)d_points + scan_offsets[0], n_scans, npts, nch,
-                          F_ELEV | F_ROT | F_CROP | F_RING | (desc ? F_SURF : 0), desc, false, false,
-                          RawLayout{nullptr, 0, 0, 0, 0}, late ? roll_pitch : nullptr);
+    s.nscans = n_scans; s.npts = npts;
+    if (small) {  // a handful of scans: lean chain, replayed from a graph captured for this shape and input pointer
+      st = enqueue_small(ctx, s, d_pts, true, n_scans, npts, nch, k1flags, desc, false, RawLayout{nullptr, 0, 0, 0, 0});
+    } else {
+      s.lean = false;
+      st = enqueue_pipeline(ctx, s, d_pts, n_scans, npts, nch, k1flags, desc, false, false, RawLayout{nullptr, 0, 0, 0, 0},
+                            late ? roll_pitch : nullptr);
+    }
     if (st) return st;
     CK(cudaEventSynchronize(s.evDone));
+    st = lean_rerun_if_deferred(ctx, s);
+    if (st) return st;
     if (s.h_ctr->err) return fail(ctx, FE_ERR_CAPACITY, err_bits(s.h_ctr->err));
     for (int i = 0; i <= n_scans; i++) ctx->kpOffsets[i] = s.h_kpOff[i];
     ctx->bndCounts.assign(ctx->bndEps > 0.0 ? (size_t)n_scans * 4 : 0, 0);
@@ -1790,6 +1860,13 @@ int fe_debug_enable_graphs(fe_ctx_t* ctx, int32_t enable, int64_t* replays) {
   if (!ctx) return FE_ERR_INVALID;
   ctx->useGraphs = enable != 0;
   if (replays) *replays = ctx->graphReplays;
+  return FE_OK;
+}
+
+// debug / test hook: how many small sub-batches had to be run again with the whole chain of fallback kernels
+int fe_debug_lean_reruns(fe_ctx_t* ctx, int64_t* reruns) {
+  if (!ctx || !reruns) return FE_ERR_INVALID;
+  *reruns = ctx->leanReruns;
   return FE_OK;
 }
 

@@ -317,6 +317,12 @@ class FeatureExtractionNode:
         self._check(N.lib().fe_debug_enable_graphs(self._ctx, 1 if enable else 0, C.byref(n)))
         return int(n.value)
 
+    def leanReruns(self):
+        """Test hook: small sub-batches that were run again with the whole chain of fallback kernels."""
+        n = C.c_int64(0)
+        self._check(N.lib().fe_debug_lean_reruns(self._ctx, C.byref(n)))
+        return int(n.value)
+
     def forceGridClustering(self, enable=True):
         """Test hook: K2 through the grid-based kernels only (the run-based kernel's fallback and cross-check)."""
         self._check(N.lib().fe_debug_force_grid_clustering(self._ctx, 1 if enable else 0))
