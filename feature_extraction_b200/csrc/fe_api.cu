@@ -23,6 +23,7 @@ namespace {
 // launches.  Their whole chain — staging copies, kernels, result copies — is captured once per shape into a CUDA
 // graph and replayed (fe_process_batch, sub-batches of at most GRAPH_MAX_SCANS scans).
 constexpr int GRAPH_MAX_SCANS = 16;
+static_assert(GRAPH_MAX_SCANS <= 32, "k_kp_offsets_gather_small gives every scan a warp of one 1024-thread block");
 struct GraphKey {
   int nscans, nch, by, k1flags, stride, xo, yo, zo;
   int desc, wantKc, bnd, epoch, lean;
@@ -721,11 +722,15 @@ int enqueue_pipeline(fe_ctx* ctx, Slot& s, const float4* d_pts, int nscans, int6
     k_boundary_merge<<<nscans, 128, 0, s.stream>>>(s.d_kfPool, s.d_kfBase, s.d_kfCnt, P, boundary_spec(ctx), s.d_bnd);
     ctx->launches++;
   }
-  k_kp_offsets<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr);
-  ctx->launches++;
-  k_kp_gather<<<std::max(1, std::min(1024, (nscans * 8 + 255) / 256)), 256, 0, s.stream>>>(s.d_kpPool, s.d_kpBase, s.d_kpOff, nscans,
-                                                                                            s.d_kpOut, s.d_kpScan);
-  ctx->launches++;
+  if (nscans <= GRAPH_MAX_SCANS) {  // a handful of scans: offsets and ordered copy in one launch
+    k_kp_offsets_gather_small<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr, s.d_kpPool, s.d_kpBase, s.d_kpOut, s.d_kpScan);
+    ctx->launches++;
+  } else {
+    k_kp_offsets<<<1, 1024, 0, s.stream>>>(s.d_kpCnt, nscans, s.d_kpOff, s.d_ctr);
+    k_kp_gather<<<std::max(1, std::min(1024, (nscans * 8 + 255) / 256)), 256, 0, s.stream>>>(s.d_kpPool, s.d_kpBase, s.d_kpOff, nscans,
+                                                                                              s.d_kpOut, s.d_kpScan);
+    ctx->launches += 2;
+  }
   mark(ctx, s, "keypoint CSR");
   if (doDesc) {
     // K4a runs after the keypoints are known: it only keeps the surface points a keypoint can reach

@@ -1172,6 +1172,26 @@ __global__ void k_kp_gather(const float4* __restrict__ kpPool, const int* __rest
   }
 }
 
+// Both steps in one launch for a call of at most 32 scans (one block; a warp copies a scan's keypoints).
+__global__ void __launch_bounds__(1024) k_kp_offsets_gather_small(const int* __restrict__ kpCnt, int n_scans, int* __restrict__ kpOff,
+                                                                   DevCounters* ctr, const float4* __restrict__ kpPool,
+                                                                   const int* __restrict__ kpBase, float4* __restrict__ kpOut,
+                                                                   int* __restrict__ kpScan) {
+  __shared__ int sc[40];
+  __shared__ int s_off[33];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int v = (t < n_scans) ? kpCnt[t] : 0;
+  int tot;
+  const int pos = block_excl_scan<1024>(v, &tot, sc);
+  if (t < n_scans) { kpOff[t] = pos; s_off[t] = pos; }
+  if (t == 0) { kpOff[n_scans] = tot; s_off[n_scans] = tot; ctr->kp_total = tot; }
+  __syncthreads();
+  if (w < n_scans) {
+    const int o = s_off[w], n = s_off[w + 1] - o, b = kpBase[w];
+    for (int i = lane; i < n; i += 32) { kpOut[o + i] = kpPool[b + i]; kpScan[o + i] = w; }
+  }
+}
+
 // Concatenate chunk pieces (or pool pieces) of every scan into a dense CSR array.
 __global__ void k_piece_counts(const int* __restrict__ cnt, const int* __restrict__ chunk_off,
                                int n_scans, int* __restrict__ perScan) {
