@@ -244,6 +244,16 @@ class Job:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def concurrent_min(self, fn, tries):
+        """min over `tries` of (max over ranks of fn()), every try started behind a barrier: all ranks really
+        run fn at the same time in every try (a per-rank min would pick the try in which the others had finished)."""
+        best = None
+        for _ in range(tries):
+            self.barrier()
+            v = self.max_over_ranks(fn())
+            best = v if best is None else min(best, v)
+        return best
+
     def sum_over_ranks(self, x):
         if self.world == 1:
             return x
@@ -409,10 +419,10 @@ def measure(job, cfg, B, steps, warmup, cpu_sample=0, packed=False):
         out["e2e_packed_xyz"] = {"value": job.world * B / (e2e12_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e12_ms,
                                  "h2d_bytes_per_step": npts * 12 + (B + 1) * 12 + B * 36, "same_keypoints_as_float4": same12,
                                  "note": "fe_process_batch_layout with 12-byte xyz records"}
-        probe_ms = job.max_over_ranks(min(host_node.h2dProbe(pts) for _ in range(3)))
+        probe_ms = job.concurrent_min(lambda: host_node.h2dProbe(pts), 3)
         out["h2d_probe"] = {"gbs": job.world * npts * 16 / (probe_ms * 1e-3) / 1e9, "ms": probe_ms,
                             "e2e_over_probe": (npts * 16 / (e2e_ms * 1e-3)) / (npts * 16 / (probe_ms * 1e-3)),
-                            "note": "bare cudaMemcpyAsync of the same pinned points, all ranks at once, max over ranks"}
+                            "note": "bare cudaMemcpyAsync of the same pinned points, all ranks at once (every try behind a barrier), max over ranks, best of 3"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only); doubles as an in-run parity check ----
     if cpu_sample > 0 and job.rank == 0 and job.world == 1:
@@ -540,8 +550,7 @@ def measure_sweep(job, total, steps, warmup):
     e2e12_ms = job.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
     pin12.free()
     # fabric ceiling: bare pinned H2D copies of every rank's shard at the same time
-    job.barrier()
-    probe_ms = job.max_over_ranks(min(host_node.h2dProbe(pts) for _ in range(2)))
+    probe_ms = job.concurrent_min(lambda: host_node.h2dProbe(pts), 2)
     tot_pts = job.sum_over_ranks(float(npts))
     sg.close()
     host_node.close()
@@ -555,10 +564,10 @@ def measure_sweep(job, total, steps, warmup):
         "value": total / (ms_step * 1e-3), "unit": "scans/s", "ms_per_step": ms_step, "mpoints_per_s": tot_pts / (ms_step * 1e-3) / 1e6,
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e_ms, "host_gather_ms_per_step": gather_ms,
                 "h2d_bytes_per_step": int(tot_pts * 16), "keypoints_gathered": K_total, "gathered_in_scan_order": ordered,
-                "input_gbs": e2e_gbs, "note": "fe_process_batch on every rank's shard + SharedGather of all results on rank 0, timed together"},
+                "input_gbs": e2e_gbs, "note": "fe_process_batch on every rank's shard + SharedGather of all results on rank 0, timed together; host_gather_ms_per_step is the time inside the gather call, max over ranks: copies plus the wait for the slowest rank at its count exchange"},
         "e2e_packed_xyz": {"value": total / (e2e12_ms * 1e-3), "unit": "scans/s", "ms_per_step": e2e12_ms, "h2d_bytes_per_step": int(tot_pts * 12)},
         "h2d_probe": {"gbs": probe_gbs, "ms": probe_ms, "e2e_over_probe": e2e_gbs / probe_gbs,
-                      "note": "bare cudaMemcpyAsync of the same pinned shards, all ranks at once, max over ranks"},
+                      "note": "bare cudaMemcpyAsync of the same pinned shards, all ranks at once (every try behind a barrier), max over ranks, best of 2"},
         "gpu_launches": launches,
     }
 
