@@ -490,9 +490,14 @@ void launch_desc_hist(fe_ctx* ctx, Slot& s, int nscans, const DevParams& P, int 
     return v;
   }();
   // A handful of scans (the reference's one scan per callback) has too few keypoints to fill the GPU with warps:
-  // there every keypoint gets a block (several times shorter per keypoint) and the warp kernel is not launched.
-  const int warpCap = nscans <= GRAPH_MAX_SCANS ? -1 : DW_CAP;
-  if (warpCap >= 0) {  // keypoints with at most DW_CAP listed neighbours (and the empty ones): a warp each
+  // there the same algorithm runs with a block per keypoint (k_desc_hist_small), several times shorter per keypoint.
+  const int warpCap = DW_CAP;
+  if (nscans <= GRAPH_MAX_SCANS) {
+    k_desc_hist_small<<<std::min(gridKp, ctx->numSms * 4), DW_CAP, 0, s.stream>>>(
+        s.d_kpOut, s.d_kpScan, s.d_kpOff, nscans, s.d_kpNbr, s.d_sorted, s.d_scan_off, P, s.d_rho, ctx->d_lut, ctx->d_axes, ctx->axesCap,
+        s.d_keyA, s.d_kpNbrOff, s.d_kpRank, s.d_desc, descStride, descOff, s.d_ctr);
+    ctx->launches++;
+  } else {  // keypoints with at most DW_CAP listed neighbours (and the empty ones): a warp each
     static const int perSmW = []() {
       int v = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_desc_hist_warp, DW_WARPS * 32, desc_warp_smem_bytes()) != cudaSuccess) v = 2;

@@ -2296,6 +2296,100 @@ constexpr int DW_CAP = 256;     // neighbours per keypoint of the warp kernel
 constexpr int DW_WARPS = 8;
 constexpr size_t desc_warp_smem_bytes() { return (size_t)DW_WARPS * DW_CAP * 12; }
 
+// The same algorithm with a BLOCK of DW_CAP threads per keypoint (one listed neighbour per thread): what calls of a
+// handful of scans use instead of the warp kernel — their few keypoints cannot fill the GPU with warps, and a block
+// finishes one keypoint several times sooner than a warp does (latency, not throughput).
+__global__ void __launch_bounds__(DW_CAP) k_desc_hist_small(
+    const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
+    int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted,
+    const long long* __restrict__ scan_off, DevParams P, const int* __restrict__ rho,
+    const float* __restrict__ lut, const float2* __restrict__ axes, int axesCap,
+    const unsigned* __restrict__ nbrPool, const int* __restrict__ kpNbrOff, const int* __restrict__ kpRank,
+    float* __restrict__ desc, int descStride, int descOff, DevCounters* __restrict__ ctr) {
+  __shared__ unsigned long long key[DW_CAP];
+  __shared__ float wgt[DW_CAP];
+  __shared__ int s_g;
+  const int tid = threadIdx.x;
+  const int total = kpOff[n_scans];
+  for (;;) {
+    __syncthreads();  // the previous keypoint's records are no longer read
+    if (tid == 0) s_g = atomicAdd(&ctr->kw_cursor, 1);
+    __syncthreads();
+    const int g = s_g;
+    if (g >= total) break;
+    const int nb = kpNbr[g];
+    const int off = kpNbrOff[g];
+    if (nb > DW_CAP || (nb > 0 && off < 0)) continue;  // the block kernels' keypoint
+    float* out = desc + (long long)g * descStride + descOff;
+    const int rank = (nb > 0) ? kpRank[g] : 0;
+    if (nb == 0 || rank >= axesCap) {  // no neighbour (or non-finite keypoint): NaN row (3dsc.hpp)
+      if (nb > 0 && tid == 0) atomicOr(&ctr->err, ERR_AXIS_CAP);
+      for (int i = tid; i < FE_DESC_LEN; i += DW_CAP) out[i] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    const int s = kpScan[g];
+    const float4 o = kpOut[g];
+    const long long base = scan_off[s];
+    const float4* so = sorted + base;
+    const int* rh = rho + base;
+    const float2 ax = axes[rank];
+    int np2 = 32;
+    while (np2 < nb) np2 <<= 1;
+    // records: (bin | d2 | point index) keys, a neighbour without a contribution sorts to the end
+    bool has = false;
+    if (tid < np2) {
+      unsigned long long k = ~0ull;
+      float wv = 0.f;
+      if (tid < nb) {
+        const int i = (int)nbrPool[off + tid];
+        const float4 q = so[i];
+        const float d2 = l2_simple(o.x, o.y, o.z, q.x, q.y, q.z);
+        int bin;
+        has = shape_context_contribution(o, q, d2, ax.x, ax.y, P, lut, rh[i], bin, wv);
+        if (has)
+          k = ((unsigned long long)bin << 52) | ((unsigned long long)__float_as_uint(d2) << 20) |
+              (unsigned long long)((unsigned)__float_as_int(q.w) & 0xFFFFFu);
+        else
+          wv = 0.f;
+      }
+      key[tid] = k; wgt[tid] = wv;
+    }
+    // the row's zeros go out while the records are sorted
+    if ((((unsigned long long)out) & 15ull) == 0ull) {
+      float4* o4 = reinterpret_cast<float4*>(out);
+      for (int i = tid; i < FE_DESC_LEN / 4; i += DW_CAP) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int i = tid; i < FE_DESC_LEN; i += DW_CAP) out[i] = 0.0f;
+    }
+    const int n = __syncthreads_count(has);
+    // bitonic sort of (key, weight), ascending
+    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        if (tid < (np2 >> 1)) {
+          const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));  // lower index of the pair
+          const int l = i | j;
+          const bool up = (i & k2) == 0;
+          const unsigned long long a = key[i], b = key[l];
+          if ((a > b) == up) {
+            key[i] = b; key[l] = a;
+            const float wa = wgt[i]; wgt[i] = wgt[l]; wgt[l] = wa;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // every bin's sum in key order (the barriers above order these stores after the zeros)
+    if (tid < n) {
+      const unsigned bin = (unsigned)(key[tid] >> 52);
+      if (tid == 0 || (unsigned)(key[tid - 1] >> 52) != bin) {
+        float acc = 0.0f;
+        for (int t = tid; t < n && (unsigned)(key[t] >> 52) == bin; t++) acc = __fadd_rn(acc, wgt[t]);
+        out[bin] = acc;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(DW_WARPS * 32) k_desc_hist_warp(
     const float4* __restrict__ kpOut, const int* __restrict__ kpScan, const int* __restrict__ kpOff,
     int n_scans, const int* __restrict__ kpNbr, const float4* __restrict__ sorted,
