@@ -395,6 +395,7 @@ int stage_scans(fe_ctx* ctx, Slot& s, const int64_t* offs, const double* rp, int
     s.h_chunk_off[i] = nch;
     const int64_t nc = (n + CH - 1) / CH;
     if (nc > (int64_t)s.capChunks - nch) return fail(ctx, FE_ERR_CAPACITY, "sub-batch exceeds the chunk capacity");
+    if (nc >= (1 << 20)) return fail(ctx, FE_ERR_CAPACITY, "a scan of more than 2^31 points");  // k_chunk_table packs (chunk << 12) | points
     nch += (int)nc;
     if (deferRot) continue;  // enqueue_pipeline computes the matrices range by range (lateRp)
     if (rp) leveling_matrix(rp[2 * i], rp[2 * i + 1], s.h_rot + 9 * i);

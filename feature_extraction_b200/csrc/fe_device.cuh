@@ -50,21 +50,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                : "memory");
 }
 
-// Largest s in [0, n) with off[s] <= key (off non-decreasing, off[0] <= key), found by one full warp as
-// a 32-ary search: three dependent rounds of loads for 10^4 entries where a scalar bisection needs 14.
-__device__ __forceinline__ int warp_search_le(const int* __restrict__ off, int n, int key, int lane) {
-  int lo = 0, hi = n;  // the answer is in [lo, hi)
-  while (hi - lo > 1) {
-    const int step = (hi - lo + 31) >> 5;
-    const int idx = lo + lane * step;
-    const bool le = idx < hi && __ldg(off + idx) <= key;
-    const int k = __popc(__ballot_sync(0xFFFFFFFFu, le));  // lanes 0..k-1 (lane 0 always)
-    lo += (k - 1) * step;
-    hi = min(hi, lo + step);
-  }
-  return lo;
-}
-
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   asm volatile(
       "{\n"
