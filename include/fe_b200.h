@@ -128,7 +128,10 @@ int fe_process_batch_layout(fe_ctx_t* ctx, const void* points, const fe_point_la
 int fe_imu_to_roll_pitch(const double quat_xyzw[4], int32_t cloud_leveling, double* roll, double* pitch);
 
 /* Same, but `d_points` is already resident in device memory and the results stay on the
- * device (keypoint_offsets is still host memory).  Must fit one sub-batch. */
+ * device (keypoint_offsets is still host memory).  Must fit one sub-batch.
+ * Calls of a handful of scans (<= 16; also through fe_process_batch) are replayed from a CUDA graph
+ * captured the second time a shape is seen — here the shape includes `d_points`, so a caller that
+ * keeps refilling the same device buffer gets the replay.  Results do not depend on the route. */
 int fe_process_batch_device(fe_ctx_t* ctx, const fe_point_t* d_points,
                             const int64_t* scan_offsets, const double* roll_pitch,
                             int32_t n_scans, fe_batch_result_t* out);
