@@ -33,3 +33,7 @@ def one(name, cfg, scan_index, params):
 if __name__ == "__main__":
     one("config1_scan0_launch_playback", 1, 0, ob.launch_playback())
     one("config2_scan5_node_default", 2, 5, ob.node_default())
+    one("config3_scan2_dense_urban", 3, 2, ob.node_default())
+    p4 = ob.node_default()
+    p4.descriptor_radius = 5.0
+    one("config4_scan1_descriptor_radius_5", 4, 1, p4)
